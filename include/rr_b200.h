@@ -1,0 +1,254 @@
+/* rr_b200.h — public C-ABI of librr_b200.so, the B200-native replacement for the request-router
+ * hot path of aws-samples/sample-resilient-llm-inference.
+ *
+ * The reference has NO native/FFI boundary: its hot path is `litellm.Router` (un-vendored
+ * dependency, reference pyproject.toml:8) configured by reference config/config.yaml:35-108,
+ * launched by reference bin/start-gateway.sh:54 and called over HTTP from
+ * reference src/demo_load_balancing.py:106-110, src/demo_fallback.py:143-147 and
+ * src/demo_quota_isolation.py:52-56; tokens are produced by the remote bedrock:InvokeModel call
+ * (reference iam/policy.json:8, src/demo_cris.py:233-238).  Every entry point below names the
+ * reference interface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain C types only; integer return codes (no exceptions cross the ABI);
+ * caller-owned buffers; `stream` arguments are cudaStream_t passed as void* (NULL = legacy
+ * default stream).  All functions return RR_OK (0) on success.
+ */
+#ifndef RR_B200_H
+#define RR_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Return codes.  RR_RATE_LIMITED is what the Python host maps to HTTP 429 / RateLimitError
+ * (reference src/demo_quota_isolation.py:80, src/demo_fallback.py:184). */
+enum {
+    RR_OK = 0,
+    RR_RATE_LIMITED = 1,      /* no deployment admitted the request (rpm/tpm/cooldown) -> 429 */
+    RR_NO_GROUP = 2,          /* unknown model group -> 400 */
+    RR_INTERNAL = 3,          /* -> 500 */
+    RR_INVALID_ARGUMENT = 4,
+    RR_CUDA_ERROR = 5,
+    RR_TIMEOUT = 6,
+    RR_BACKEND_FAILED = 7     /* injected/real backend failure with no fallback left -> 500 */
+};
+
+const char* rr_version(void);
+const char* rr_strerror(int rc);
+/* Last CUDA error string seen by the library on this thread (diagnostics). */
+const char* rr_last_cuda_error(void);
+
+/* ================================================================================================
+ * 1. Router: admission + rpm/tpm bucket debit + backend pick + cooldown + fallback chain (K1).
+ *    Replaces litellm.Router as configured by reference config/config.yaml:35-108
+ *    (model_list[].{model_name,litellm_params,rpm,tpm}; router_settings.{routing_strategy,
+ *    enable_pre_call_checks,allowed_fails,cooldown_time,fallbacks}).
+ *    State lives in HBM; one kernel launch processes an ordered trace of events with the same
+ *    result as processing them one at a time (serialised-trace semantics). */
+
+enum {                       /* router_settings.routing_strategy (reference config.yaml:101) */
+    RR_STRATEGY_SIMPLE_SHUFFLE = 0,
+    RR_STRATEGY_LEAST_BUSY = 1,
+    RR_STRATEGY_ROUND_ROBIN = 2   /* reference src/demo_account_sharding.py:335-343 (req_id % n) */
+};
+
+enum { RR_EV_ADMIT = 0, RR_EV_DONE = 1, RR_EV_FAIL = 2 };
+
+typedef struct rr_deployment_desc {
+    int32_t group;           /* index of model_name (reference config.yaml:36,44,...) */
+    int32_t rpm;             /* requests / minute, <0 = unlimited (config.yaml:41) */
+    int32_t tpm;             /* tokens / minute, <0 = unlimited (config.yaml:42) */
+    int32_t weight;          /* simple-shuffle weight, <0 = unset */
+    int32_t replica;         /* GPU / engine index that serves this deployment */
+    int32_t reserved;
+} rr_deployment_desc;
+
+typedef struct rr_router_settings {
+    int32_t strategy;               /* RR_STRATEGY_* */
+    int32_t enable_pre_call_checks; /* config.yaml:102 */
+    int32_t allowed_fails;          /* config.yaml:103 */
+    int32_t cooldown_ms;            /* config.yaml:104 (seconds * 1000) */
+    int32_t weight_by;              /* 0 = uniform, 1 = weight, 2 = rpm, 3 = tpm (simple-shuffle) */
+    int32_t reserved[3];
+} rr_router_settings;
+
+typedef struct rr_event {
+    int32_t type;            /* RR_EV_* */
+    int32_t target;          /* ADMIT: group index; DONE/FAIL: deployment index */
+    int32_t tokens;          /* ADMIT: prompt tokens; DONE: completion tokens */
+    int32_t chain_start;     /* ADMIT: 0 = try the group itself first, k = start at k-th fallback */
+    int64_t now_ms;          /* injectable clock, milliseconds */
+} rr_event;
+
+typedef struct rr_decision {
+    int32_t status;          /* RR_OK / RR_RATE_LIMITED / RR_NO_GROUP */
+    int32_t deployment;      /* picked deployment, -1 if none */
+    int32_t served_group;    /* group that served (differs from target when fell back) */
+    int32_t chain_pos;       /* 0 = primary, k = k-th fallback */
+} rr_decision;
+
+typedef struct rr_deployment_state {
+    int64_t window;          /* minute index of the rpm/tpm window */
+    int32_t req_count;
+    int32_t tok_count;
+    int64_t fail_window;
+    int32_t fail_count;
+    int32_t inflight;
+    int64_t cooldown_until_ms;
+    int64_t total_admitted;
+} rr_deployment_state;
+
+typedef struct rr_router rr_router;
+
+/* fallback chains in CSR form: group g falls back to fb_groups[fb_offsets[g] .. fb_offsets[g+1])
+ * (reference config.yaml:105-108). */
+int rr_router_create(const rr_deployment_desc* deployments, int n_deployments, int n_groups,
+                     const int32_t* fb_offsets, const int32_t* fb_groups,
+                     const rr_router_settings* settings, uint64_t seed, int device,
+                     rr_router** out);
+void rr_router_destroy(rr_router* r);
+/* Host buffers: copies events H2D, runs the admission kernel, copies decisions D2H. Thread-safe. */
+int rr_router_process(rr_router* r, const rr_event* events, int n_events, rr_decision* decisions);
+/* Device buffers already resident in HBM; asynchronous on `stream`. */
+int rr_router_process_device(rr_router* r, const rr_event* d_events, int n_events,
+                             rr_decision* d_decisions, void* stream);
+int rr_router_snapshot(rr_router* r, rr_deployment_state* out /* [n_deployments] */);
+/* Re-seed the MT19937 stream exactly like CPython random.seed(int). */
+int rr_router_seed(rr_router* r, uint64_t seed);
+
+/* ================================================================================================
+ * 2. Prompt token count (K2).  Replaces litellm.token_counter as used for tpm accounting
+ *    (no call site in the reference tree; tpm values at reference config.yaml:42).
+ *    Counts tokens of the library's byte-level tokenizer: n_tokens = n_utf8_bytes + 1 (BOS). */
+int rr_count_tokens(const uint8_t* text, size_t n_bytes, int32_t* n_tokens);
+int rr_tokenize(const uint8_t* text, size_t n_bytes, int32_t vocab, int32_t* ids, int32_t max_ids,
+                int32_t* n_ids);
+
+/* ================================================================================================
+ * 3. Kernel-level entry points (used by the parity tests and the engine).
+ *    Replaces the remote bedrock:InvokeModel prefill/decode (reference iam/policy.json:8,
+ *    src/demo_cris.py:233-238).  All pointers are device pointers. */
+
+enum { RR_OUT_ROWMAJOR_BF16 = 0, RR_OUT_TRANSPOSED_F32 = 1 };
+
+/* D[a,b] = sum_k A[a,k] B[b,k] on tcgen05 tensor cores (bf16 in, fp32 accumulate).
+ * mode RR_OUT_ROWMAJOR_BF16:  out bf16 [rowsA, ldo], out[a*ldo + b]         (splits must be 1)
+ * mode RR_OUT_TRANSPOSED_F32: out fp32 [splits, ld_rows, ldo], out[(z*ld_rows + b)*ldo + a]
+ * bn = tile width along B rows: 16/32/64/128/256. */
+int rr_gemm_bf16(const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB, int K,
+                 void* out, int ldo, int ld_rows, int splits, int mode, int bn, void* stream);
+
+int rr_op_embed(const int32_t* ids, const void* table, float* x, int rows, int hidden,
+                const int32_t* row_active, void* stream);
+int rr_op_add_rmsnorm(float* x, const void* part, int part_is_bf16, int n_splits,
+                      long long split_stride, int part_ld, const void* w, void* xn, int rows,
+                      int hidden, float eps, void* stream);
+int rr_op_silu_mul(const void* gu, int is_bf16, int n_splits, long long split_stride, int ld,
+                   void* act, int rows, int inter, void* stream);
+int rr_op_rope_kv(const void* qkv, int is_bf16, int n_splits, long long split_stride, int ld,
+                  void* q_out, void* k_cache, void* v_cache, const int32_t* slot,
+                  const int32_t* pos, int rows, int n_heads, int n_kv_heads, int ctx_max,
+                  float theta, void* stream);
+int rr_op_argmax(const float* logits, int ld, int rows, int vocab, int32_t* out_tok,
+                 float* out_val, const int32_t* row_active, int32_t* pos_inc, void* stream);
+int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
+                      const int32_t* slot, const int32_t* pos, int rows, int n_heads,
+                      int n_kv_heads, int ctx_max, float scale, int kv_splits, void* stream);
+int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
+                       const int32_t* seq_start, const int32_t* seq_slot, int n_seqs, int max_len,
+                       int n_heads, int n_kv_heads, int ctx_max, float scale, void* stream);
+
+/* ================================================================================================
+ * 4. Engine: one model replica on one GPU (prefill + continuous-batching greedy decode).
+ *    Replaces one `litellm_params.model: bedrock/...` deployment (reference config.yaml:39,47,54,
+ *    62,69,77,84,91). */
+
+typedef struct rr_model_desc {
+    int32_t vocab, hidden, inter, n_layers, n_heads, n_kv_heads, head_dim;
+    float rope_theta, rms_eps;
+} rr_model_desc;
+
+/* Device pointers to bf16 weights, row-major [out_features, in_features] like torch nn.Linear.
+ * wqkv = concat(q_proj, k_proj, v_proj) rows; wgu = concat(gate_proj, up_proj) rows. */
+typedef struct rr_model_weights {
+    const void* embed;            /* [vocab, hidden] */
+    const void* lm_head;          /* [vocab, hidden] */
+    const void* final_norm;       /* [hidden] */
+    const void* const* wqkv;      /* n_layers x [(n_heads + 2 n_kv_heads) * head_dim, hidden] */
+    const void* const* wo;        /* n_layers x [hidden, n_heads * head_dim] */
+    const void* const* wgu;       /* n_layers x [2 * inter, hidden] */
+    const void* const* wdown;     /* n_layers x [hidden, inter] */
+    const void* const* norm_attn; /* n_layers x [hidden] */
+    const void* const* norm_mlp;  /* n_layers x [hidden] */
+} rr_model_weights;
+
+typedef struct rr_engine rr_engine;
+
+typedef struct rr_engine_opts {
+    int32_t device;
+    int32_t max_batch;            /* decode rows / KV slots (<= 256) */
+    int32_t ctx_max;              /* tokens per KV slot */
+    int32_t max_prefill_tokens;   /* tokens per prefill chunk */
+    int32_t use_cuda_graph;       /* capture the decode step */
+    int32_t fail_seed;            /* fault injection: seed of the Bernoulli failure mask */
+    float fail_prob;              /* fault injection: P(request fails) (BASELINE config #4) */
+    int32_t reserved[4];
+} rr_engine_opts;
+
+int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w,
+                     const rr_engine_opts* opts, rr_engine** out);
+void rr_engine_destroy(rr_engine* e);
+
+/* Low-level synchronous steps (parity tests).  Host buffers.
+ * prefill: n_seqs prompts concatenated in `ids`; seq_start[n_seqs+1]; slots[n_seqs] = KV slots.
+ *          Writes first generated token per prompt to first_tok[n_seqs].
+ *          If logits_out != NULL: fp32 [n_seqs, vocab] last-position logits. */
+int rr_engine_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_start,
+                      const int32_t* slots, int n_seqs, int32_t* first_tok, float* logits_out);
+/* One decode step for the given slots, feeding tok[i] at position pos[i]; returns next tokens and
+ * optionally fp32 logits [n, vocab]. */
+int rr_engine_decode_step(rr_engine* e, const int32_t* slots, const int32_t* tok,
+                          const int32_t* pos, int n, int32_t* next_tok, float* logits_out);
+
+/* Asynchronous serving interface (the call shape of chat.completions.create: reference
+ * src/demo_load_balancing.py:106-110).  submit is thread-safe and non-blocking; wait blocks
+ * (release the GIL around it). */
+typedef struct rr_completion {
+    uint64_t ticket;
+    int32_t status;               /* RR_OK / RR_BACKEND_FAILED / RR_TIMEOUT */
+    int32_t n_prompt;
+    int32_t n_generated;
+    int32_t reserved;
+    double t_submit_s, t_first_token_s, t_done_s;   /* engine monotonic clock */
+} rr_completion;
+
+int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int max_new_tokens,
+                     uint64_t* ticket);
+int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_completion* out,
+                   int32_t* tokens_out, int max_tokens_out);
+/* Closed-batch convenience used by bench.py: submit all, wait all. prompts are host buffers
+ * (pinned or pageable); the H2D copies happen inside. */
+int rr_engine_run_batch(rr_engine* e, const int32_t* prompt_ids, const int32_t* prompt_start,
+                        int n_requests, int max_new_tokens, rr_completion* out,
+                        int32_t* tokens_out /* [n_requests, max_new_tokens] */);
+double rr_engine_now(rr_engine* e);
+
+typedef struct rr_engine_stats {
+    uint64_t kernel_launches;     /* library kernels launched (graph replays count their nodes) */
+    uint64_t decode_steps, prefill_chunks, prefill_tokens, generated_tokens;
+    double decode_ms_total, prefill_ms_total;   /* CUDA-event time on the engine stream */
+    int32_t active_rows, queued;
+    uint64_t h2d_bytes, d2h_bytes;
+} rr_engine_stats;
+int rr_engine_get_stats(rr_engine* e, rr_engine_stats* out);
+int rr_engine_reset_stats(rr_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RR_B200_H */

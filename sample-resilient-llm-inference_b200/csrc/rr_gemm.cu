@@ -1,0 +1,344 @@
+// rr_gemm.cu — the path's one dense contraction (QKV / O / gate-up / down / lm_head projections)
+// on 5th-generation tensor cores: tcgen05.mma (UTCHMMA) with fp32 accumulators in TMEM,
+// operands staged by TMA (UTMALDG) into 128B-swizzled shared memory, persistent
+// warp-specialised CTAs (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered TMEM.
+//
+//   D[a, b] = sum_k A[a, k] * B[b, k]          A: [rowsA, K] bf16, B: [rowsB, K] bf16 (both K-major)
+//
+// Two orientations of the same kernel:
+//   * prefill  (OUT_ROWMAJOR_BF16):  A = activations [T, K], B = weight [N, K]  -> C[T, N] bf16
+//   * decode   (OUT_TRANSPOSED_F32): A = weight [N, K] (UMMA M side, streamed once from HBM),
+//                                    B = activations [batch<=BN, K]; split-K over gridDim work
+//                                    items; fp32 partials P[z][b][n] reduced by the consumer
+//                                    kernel (rr_elementwise.cu).
+//
+// Replaces: the remote bedrock:InvokeModel call (reference iam/policy.json:8,
+// src/demo_cris.py:233-238) — there is no reference kernel; see DESIGN.md §kernels.
+#include "rr_ptx.cuh"
+#include "rr_kernels.h"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace rr {
+
+constexpr int BLOCK_A = 128;   // UMMA M
+constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_A = 16;    // raster group: 16 A tiles share the streamed B tiles through L2
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStageBytesA = BLOCK_A * BLOCK_K * 2;
+    static constexpr int kStageBytesB = BN * BLOCK_K * 2;
+    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+    static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr uint32_t kTmemCols =
+        (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+    int a_tile, b_tile, z;
+};
+
+__device__ __forceinline__ TileCoord decode_work(int w, int tilesA, int tilesB, int splits) {
+    TileCoord t;
+    t.z = w % splits;
+    int q = w / splits;
+    int per_group = GROUP_A * tilesB;
+    int g = q / per_group;
+    int r = q - g * per_group;
+    int a0 = g * GROUP_A;
+    int ga = min(GROUP_A, tilesA - a0);
+    t.a_tile = a0 + r % ga;
+    t.b_tile = r / ga;
+    return t;
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  void* __restrict__ out, int rowsA, int rowsB, int K, int splits, int ldo,
+                  int ld_rows) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + kStages * Cfg::kStageBytesA;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
+    const int tilesB = (rowsB + BN - 1) / BN;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int n_work = tilesA * tilesB * splits;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full[s], 1);
+                mbar_init(&tmem_empty[s], 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            // Streamed-once operand (decode weights) should not displace the KV cache in L2;
+            // the small re-read operand is kept.
+            const uint64_t polA = (MODE == OUT_TRANSPOSED_F32) ? l2_policy_evict_first()
+                                                               : l2_policy_evict_last();
+            const uint64_t polB = l2_policy_evict_last();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+                const int kb0 = (int)(((long long)kblocks * t.z) / splits);
+                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage],
+                                     kb * BLOCK_K, t.a_tile * BLOCK_A, polA);
+                    tma_load_2d_hint(smemB + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage],
+                                     kb * BLOCK_K, t.b_tile * BN, polB);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_A, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+                const int kb0 = (int)(((long long)kblocks * t.z) / splits);
+                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t adesc =
+                        umma_desc_sw128_kmajor(smem_u32(smemA + stage * Cfg::kStageBytesA));
+                    const uint64_t bdesc =
+                        umma_desc_sw128_kmajor(smem_u32(smemB + stage * Cfg::kStageBytesB));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B inside the swizzle row: +2 in 16-byte units
+                        umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                     (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // smem slot free once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);         // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int a_row = t.a_tile * BLOCK_A + row_in_tile;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            constexpr int CH = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += CH) {
+                uint32_t v[32];
+                if constexpr (CH == 32) {
+                    tmem_ld_32x32b_x32(taddr0 + c, v);
+                } else {
+                    uint32_t v16[16];
+                    tmem_ld_32x32b_x16(taddr0 + c, v16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v16[j];
+                }
+                tmem_ld_wait();
+                const int b0 = t.b_tile * BN + c;
+                if constexpr (MODE == OUT_ROWMAJOR_BF16) {
+                    if (a_row < rowsA) {
+                        __nv_bfloat16* dst =
+                            reinterpret_cast<__nv_bfloat16*>(out) + (size_t)a_row * ldo + b0;
+                        if (b0 + CH <= rowsB) {
+#pragma unroll
+                            for (int j = 0; j < CH; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                                pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                                pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                                *reinterpret_cast<uint4*>(dst + j) = pk;
+                            }
+                        } else {
+                            for (int j = 0; j < CH; ++j)
+                                if (b0 + j < rowsB) dst[j] = __float2bfloat16(__uint_as_float(v[j]));
+                        }
+                    }
+                } else {
+                    float* dst = reinterpret_cast<float*>(out);
+                    if (a_row < rowsA) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const int b = b0 + j;
+                            if (b < rowsB)
+                                dst[((size_t)t.z * ld_rows + b) * ldo + a_row] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+// [rows, K] bf16 row-major (K contiguous, row pitch ld elements) -> TMA map with box {64, box_rows}.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return RR_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? RR_OK : RR_ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+template <int BN, int MODE>
+static int launch_one(const GemmPlan& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_bf16_tcgen05<BN, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return RR_ERR_CUDA;
+        attr_set = true;
+    }
+    const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
+    const int tilesB = (p.rowsB + BN - 1) / BN;
+    const int n_work = tilesA * tilesB * p.splits;
+    int grid = n_work < num_sms() ? n_work : num_sms();
+    if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
+    kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(p.tmA, p.tmB, p.out, p.rowsA, p.rowsB, p.K,
+                                                      p.splits, p.ldo, p.ld_rows);
+    return cudaGetLastError() == cudaSuccess ? RR_OK : RR_ERR_CUDA;
+}
+
+int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
+                   int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn) {
+    if (K % 8 != 0 || ldA % 8 != 0 || ldB % 8 != 0) return RR_ERR_ARG;
+    if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256)) return RR_ERR_ARG;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    if (splits < 1) splits = 1;
+    if (splits > kblocks) splits = kblocks;
+    if (mode == OUT_ROWMAJOR_BF16 && (splits != 1 || ldo % 8 != 0)) return RR_ERR_ARG;
+    p->rowsA = rowsA; p->rowsB = rowsB; p->K = K; p->out = out; p->ldo = ldo; p->ld_rows = ld_rows;
+    p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
+    int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
+    if (rc != RR_OK) return rc;
+    return make_tmap_bf16_2d(&p->tmB, B, rowsB, K, ldB, bn);
+}
+
+int gemm_launch(const GemmPlan& p, cudaStream_t st) {
+#define RR_CASE(BN_)                                                                   \
+    case BN_:                                                                          \
+        return p.mode == OUT_ROWMAJOR_BF16 ? launch_one<BN_, OUT_ROWMAJOR_BF16>(p, st) \
+                                           : launch_one<BN_, OUT_TRANSPOSED_F32>(p, st);
+    switch (p.bn) {
+        RR_CASE(16)
+        RR_CASE(32)
+        RR_CASE(64)
+        RR_CASE(128)
+        RR_CASE(256)
+    }
+#undef RR_CASE
+    return RR_ERR_ARG;
+}
+
+}  // namespace rr

@@ -1,0 +1,93 @@
+// rr_kernels.h — internal (C++) declarations shared by the .cu files of librr_b200.so.
+// The public C-ABI is include/rr_b200.h; nothing here crosses the library boundary.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/rr_b200.h"
+
+namespace rr {
+
+#define RR_ERR_ARG RR_INVALID_ARGUMENT
+#define RR_ERR_CUDA RR_CUDA_ERROR
+
+enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1 };
+
+struct GemmPlan {
+    CUtensorMap tmA, tmB;
+    void* out;
+    int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas;
+};
+
+int num_sms();
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows);
+int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
+                   int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn);
+int gemm_launch(const GemmPlan& p, cudaStream_t st);
+
+// ---- elementwise / normalisation (rr_elementwise.cu) -------------------------------------------
+// `part` inputs are the GEMM outputs: either fp32 split-K partials P[z][row][col] (n_splits >= 1,
+// part_is_bf16 = 0, split stride = split_stride elements) or a single bf16 matrix.
+struct PartIn {
+    const void* ptr;
+    int is_bf16;
+    int n_splits;
+    long long split_stride;   // elements between split planes
+    int ld;                   // row pitch in elements
+};
+
+void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int rows, int hidden,
+                  const int32_t* row_active, cudaStream_t st);
+// x[row] (+)= sum_z part[z][row]; xn[row] = rmsnorm(x[row]) * w   (part.ptr may be null: norm only)
+void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
+                        int hidden, float eps, cudaStream_t st);
+// act[row, j] = silu(gate[row, j]) * up[row, j]; gate = cols [0, inter), up = cols [inter, 2*inter)
+void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st);
+// qkv (partials) -> RoPE(q), RoPE(k); q -> q_out [rows, n_heads*128] bf16; k, v -> KV cache.
+struct RopeArgs {
+    PartIn qkv;
+    __nv_bfloat16* q_out;
+    __nv_bfloat16* k_cache;   // [slot][kv_head][ctx_max][128]
+    __nv_bfloat16* v_cache;
+    const int32_t* slot;      // per row: KV slot (or -1 = skip)
+    const int32_t* pos;       // per row: position
+    int rows, n_heads, n_kv_heads, ctx_max;
+    float theta;
+};
+void launch_rope_kv(const RopeArgs& a, cudaStream_t st);
+// argmax over fp32 logits [rows, vocab] (partials with n_splits = 1); writes next token, and if
+// advance != 0: pos[row]++ (decode bookkeeping folded into the same launch).
+void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
+                   const int32_t* row_active, int32_t* pos_inc, cudaStream_t st);
+
+// ---- attention (rr_attn.cu) ---------------------------------------------------------------------
+struct DecodeAttnArgs {
+    const __nv_bfloat16* q;   // [rows, n_heads*128]
+    const __nv_bfloat16* k_cache;
+    const __nv_bfloat16* v_cache;
+    __nv_bfloat16* out;       // [rows, n_heads*128]
+    const int32_t* slot;      // per row
+    const int32_t* pos;       // per row: position of the current token (ctx = pos + 1)
+    int rows, n_heads, n_kv_heads, ctx_max;
+    float scale;
+    float* ws;                // split-KV workspace (may be null when kv_splits == 1)
+    int kv_splits;
+};
+void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st);
+size_t decode_attn_ws_bytes(int rows, int n_heads, int kv_splits);
+
+struct PrefillAttnArgs {
+    const __nv_bfloat16* q;   // [T, n_heads*128] (RoPE applied)
+    const __nv_bfloat16* k_cache;
+    const __nv_bfloat16* v_cache;
+    __nv_bfloat16* out;       // [T, n_heads*128]
+    const int32_t* seq_start; // [n_seqs+1] token offsets into T
+    const int32_t* seq_slot;  // [n_seqs]
+    int n_seqs, max_len, n_heads, n_kv_heads, ctx_max;
+    float scale;
+};
+void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st);
+
+}  // namespace rr

@@ -1,0 +1,74 @@
+"""Parity of the tcgen05 GEMM (rr_gemm_bf16) against a torch fp32 reference of the same op.
+Tolerance: bf16 inputs are exact in both; fp32 accumulation order differs -> |err| <= 2e-3 * sqrt(K)
+relative to |a||b| scale for fp32 out, plus one bf16 rounding (2^-8 relative) for bf16 out."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(A, B, mode, bn, splits=1, ld_rows=None):
+    from rr_b200 import _lib
+    rowsA, K = A.shape
+    rowsB = B.shape[0]
+    if mode == 0:
+        out = torch.full((rowsA, rowsB), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ldo, ldr = rowsB, 0
+    else:
+        ldr = ld_rows or rowsB
+        out = torch.full((splits, ldr, rowsA), float("nan"), device="cuda", dtype=torch.float32)
+        ldo = rowsA
+    rc = _lib.lib.rr_gemm_bf16(A.data_ptr(), rowsA, A.stride(0), B.data_ptr(), rowsB, B.stride(0),
+                               K, out.data_ptr(), ldo, ldr, splits, mode, bn, None)
+    _lib.check(rc, "rr_gemm_bf16")
+    torch.cuda.synchronize()
+    return out
+
+
+CASES_T = [  # decode orientation: rowsA = weight rows, rowsB = batch
+    (128, 16, 64, 16, 1), (256, 64, 512, 64, 1), (384, 33, 4096, 64, 3), (4096, 64, 4096, 64, 4),
+    (1000, 7, 320, 16, 2), (6144, 64, 4096, 64, 3), (512, 128, 1024, 128, 2), (640, 20, 14336, 32, 7),
+]
+
+
+@pytest.mark.parametrize("rowsA,rowsB,K,bn,splits", CASES_T)
+def test_gemm_transposed_f32(rowsA, rowsB, K, bn, splits):
+    g = torch.Generator(device="cuda").manual_seed(rowsA * 7 + rowsB)
+    A = (torch.randn(rowsA, K, device="cuda", generator=g) * 0.05).bfloat16()
+    B = torch.randn(rowsB, K, device="cuda", generator=g).bfloat16()
+    out = _gemm(A, B, 1, bn, splits)
+    got = out.sum(0)                      # [rowsB, rowsA]
+    ref = B.float() @ A.float().t()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-3 * scale + 1e-4, (err, scale)
+
+
+CASES_R = [(128, 256, 64, 256), (512, 6144, 4096, 256), (1000, 520, 256, 128), (2048, 4096, 4096, 256),
+           (130, 72, 128, 64), (4096, 28672, 4096, 256)]
+
+
+@pytest.mark.parametrize("rowsA,rowsB,K,bn", CASES_R)
+def test_gemm_rowmajor_bf16(rowsA, rowsB, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(rowsA + rowsB)
+    A = torch.randn(rowsA, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(rowsB, K, device="cuda", generator=g) * 0.05).bfloat16()
+    got = _gemm(A, B, 0, bn).float()
+    ref = A.float() @ B.float().t()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 6e-3 * scale + 1e-4, (err, scale)
+
+
+def test_gemm_exact_small_integers():
+    """Integer-valued operands: every product and partial sum is exact in fp32 -> bit-exact."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randint(-4, 5, (256, 512), device="cuda", generator=g).bfloat16()
+    B = torch.randint(-4, 5, (64, 512), device="cuda", generator=g).bfloat16()
+    got = _gemm(A, B, 1, 64, 2).sum(0)
+    ref = B.float() @ A.float().t()
+    assert torch.equal(got, ref)
