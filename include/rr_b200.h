@@ -120,6 +120,8 @@ int rr_router_process_device(rr_router* r, const rr_event* d_events, int n_event
 int rr_router_snapshot(rr_router* r, rr_deployment_state* out /* [n_deployments] */);
 /* Re-seed the MT19937 stream exactly like CPython random.seed(int). */
 int rr_router_seed(rr_router* r, uint64_t seed);
+/* Host-only: the MT19937 state (624 words + index) CPython's random.seed(seed) produces. */
+int rr_mt_seed_state(uint64_t seed, uint32_t* out625);
 
 /* ================================================================================================
  * 2. Prompt token count (K2).  Replaces litellm.token_counter as used for tpm accounting

@@ -73,3 +73,94 @@ RR_API int rr_gemm_bf16(const void* A, int rowsA, int ldA, const void* B, int ro
     if (rc != RR_OK) note_cuda_error(cudaPeekAtLastError());
     return rc;
 }
+
+static PartIn mk_part(const void* p, int is_bf16, int n_splits, long long split_stride, int ld) {
+    PartIn r;
+    r.ptr = p; r.is_bf16 = is_bf16; r.n_splits = n_splits < 1 ? 1 : n_splits;
+    r.split_stride = split_stride; r.ld = ld;
+    return r;
+}
+
+RR_API int rr_op_embed(const int32_t* ids, const void* table, float* x, int rows, int hidden,
+                       const int32_t* row_active, void* stream) {
+    if (!ids || !table || !x || hidden % 8) return RR_INVALID_ARGUMENT;
+    launch_embed(ids, (const __nv_bfloat16*)table, x, rows, hidden, row_active, (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_add_rmsnorm(float* x, const void* part, int part_is_bf16, int n_splits,
+                             long long split_stride, int part_ld, const void* w, void* xn, int rows,
+                             int hidden, float eps, void* stream) {
+    if (!x || !w || !xn || hidden % 4) return RR_INVALID_ARGUMENT;
+    launch_add_rmsnorm(x, mk_part(part, part_is_bf16, n_splits, split_stride, part_ld),
+                       (const __nv_bfloat16*)w, (__nv_bfloat16*)xn, rows, hidden, eps, (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_silu_mul(const void* gu, int is_bf16, int n_splits, long long split_stride, int ld,
+                          void* act, int rows, int inter, void* stream) {
+    if (!gu || !act || inter % 4) return RR_INVALID_ARGUMENT;
+    launch_silu_mul(mk_part(gu, is_bf16, n_splits, split_stride, ld), (__nv_bfloat16*)act, rows, inter,
+                    (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_rope_kv(const void* qkv, int is_bf16, int n_splits, long long split_stride, int ld,
+                         void* q_out, void* k_cache, void* v_cache, const int32_t* slot,
+                         const int32_t* pos, int rows, int n_heads, int n_kv_heads, int ctx_max,
+                         float theta, void* stream) {
+    if (!qkv || !q_out || !k_cache || !v_cache || !slot || !pos) return RR_INVALID_ARGUMENT;
+    RopeArgs a;
+    a.qkv = mk_part(qkv, is_bf16, n_splits, split_stride, ld);
+    a.q_out = (__nv_bfloat16*)q_out; a.k_cache = (__nv_bfloat16*)k_cache; a.v_cache = (__nv_bfloat16*)v_cache;
+    a.slot = slot; a.pos = pos; a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads;
+    a.ctx_max = ctx_max; a.theta = theta;
+    launch_rope_kv(a, (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_argmax(const float* logits, int ld, int rows, int vocab, int32_t* out_tok,
+                        float* out_val, const int32_t* row_active, int32_t* pos_inc, void* stream) {
+    if (!logits || !out_tok || ld % 4) return RR_INVALID_ARGUMENT;
+    launch_argmax(mk_part(logits, 0, 1, 0, ld), rows, vocab, out_tok, out_val, row_active, pos_inc,
+                  (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
+                             const int32_t* slot, const int32_t* pos, int rows, int n_heads,
+                             int n_kv_heads, int ctx_max, float scale, int kv_splits, void* stream) {
+    if (!q || !k_cache || !v_cache || !out || !slot || !pos) return RR_INVALID_ARGUMENT;
+    if (n_kv_heads <= 0 || n_heads % n_kv_heads) return RR_INVALID_ARGUMENT;
+    const int G = n_heads / n_kv_heads;
+    if (!(G == 1 || G == 2 || G == 4 || G == 8)) return RR_INVALID_ARGUMENT;
+    DecodeAttnArgs a;
+    a.q = (const __nv_bfloat16*)q; a.k_cache = (const __nv_bfloat16*)k_cache;
+    a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.slot = slot; a.pos = pos;
+    a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
+    a.kv_splits = kv_splits < 1 ? 1 : kv_splits; a.ws = nullptr;
+    float* ws = nullptr;
+    if (a.kv_splits > 1) {
+        cudaError_t e = cudaMallocAsync(&ws, decode_attn_ws_bytes(rows, n_heads, a.kv_splits), (cudaStream_t)stream);
+        if (e != cudaSuccess) { note_cuda_error(e); return RR_CUDA_ERROR; }
+        a.ws = ws;
+    }
+    launch_decode_attn(a, (cudaStream_t)stream);
+    if (ws) cudaFreeAsync(ws, (cudaStream_t)stream);
+    return check_last();
+}
+
+RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
+                              const int32_t* seq_start, const int32_t* seq_slot, int n_seqs,
+                              int max_len, int n_heads, int n_kv_heads, int ctx_max, float scale,
+                              void* stream) {
+    if (!q || !k_cache || !v_cache || !out || !seq_start || !seq_slot) return RR_INVALID_ARGUMENT;
+    if (n_kv_heads <= 0 || n_heads % n_kv_heads) return RR_INVALID_ARGUMENT;
+    PrefillAttnArgs a;
+    a.q = (const __nv_bfloat16*)q; a.k_cache = (const __nv_bfloat16*)k_cache;
+    a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.seq_start = seq_start;
+    a.seq_slot = seq_slot; a.n_seqs = n_seqs; a.max_len = max_len; a.n_heads = n_heads;
+    a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
+    launch_prefill_attn(a, (cudaStream_t)stream);
+    return check_last();
+}

@@ -1,0 +1,249 @@
+// rr_elementwise.cu — the HBM-bound glue between the projections: embedding gather (K3),
+// split-K reduce + residual add + RMSNorm (K4), RoPE + KV-cache append (K6), SiLU*mul,
+// greedy argmax (K11 tail).  All are row-parallel, 16-byte vectorised, fp32 math.
+// Each consumer reads the producing GEMM's output either as fp32 split-K partials
+// P[z][row][col] (decode orientation) or as one bf16 matrix (prefill orientation).
+//
+// Replaces (together with rr_gemm.cu / rr_attn.cu) the remote bedrock:InvokeModel call
+// (reference iam/policy.json:8; src/demo_cris.py:233-238).
+#include "rr_ptx.cuh"
+#include "rr_kernels.h"
+
+namespace rr {
+
+// ---- reading a GEMM output ---------------------------------------------------------------------
+// 4 consecutive columns of one row, summed over split planes.
+__device__ __forceinline__ float4 part_load4(const PartIn& p, int row, int col) {
+    if (p.is_bf16) {
+        const uint2 v = *reinterpret_cast<const uint2*>(
+            reinterpret_cast<const __nv_bfloat16*>(p.ptr) + (size_t)row * p.ld + col);
+        return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+    }
+    const float* base = reinterpret_cast<const float*>(p.ptr) + (size_t)row * p.ld + col;
+    float4 acc = *reinterpret_cast<const float4*>(base);
+    for (int z = 1; z < p.n_splits; ++z) {
+        const float4 t = *reinterpret_cast<const float4*>(base + (size_t)z * p.split_stride);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;
+}
+
+// ---- K3 embedding gather -----------------------------------------------------------------------
+__global__ void embed_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                             float* __restrict__ x, int hidden, const int32_t* __restrict__ row_active) {
+    const int row = blockIdx.x;
+    if (row_active && row_active[row] < 0) return;
+    const int id = ids[row];
+    const __nv_bfloat16* src = table + (size_t)id * hidden;
+    float* dst = x + (size_t)row * hidden;
+    for (int c = threadIdx.x * 8; c < hidden; c += blockDim.x * 8) {
+        const uint4 v = ldg_nc_v4(src + c);
+        float4 a = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+        float4 b = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+        *reinterpret_cast<float4*>(dst + c) = a;
+        *reinterpret_cast<float4*>(dst + c + 4) = b;
+    }
+}
+
+void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int rows, int hidden,
+                  const int32_t* row_active, cudaStream_t st) {
+    if (rows <= 0) return;
+    embed_kernel<<<rows, 256, 0, st>>>(ids, table, x, hidden, row_active);
+}
+
+// ---- K4 residual add + RMSNorm (+ split-K reduce) ------------------------------------------------
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
+                   __nv_bfloat16* __restrict__ xn, int hidden, float eps) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    float* xr = x + (size_t)row * hidden;
+    float ss = 0.f;
+    for (int c = threadIdx.x * 4; c < hidden; c += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<float4*>(xr + c);
+        if (part.ptr) {
+            const float4 p = part_load4(part, row, c);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            *reinterpret_cast<float4*>(xr + c) = v;
+        }
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = block_sum(ss, red);
+    const float inv = rsqrtf(ss / (float)hidden + eps);
+    __nv_bfloat16* out = xn + (size_t)row * hidden;
+    for (int c = threadIdx.x * 4; c < hidden; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);   // own writes: L1/L2 hit
+        const uint2 wv = *reinterpret_cast<const uint2*>(w + c);
+        uint2 o;
+        o.x = pack_bf16(v.x * inv * bf16_lo(wv.x), v.y * inv * bf16_hi(wv.x));
+        o.y = pack_bf16(v.z * inv * bf16_lo(wv.y), v.w * inv * bf16_hi(wv.y));
+        *reinterpret_cast<uint2*>(out + c) = o;
+    }
+}
+
+void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
+                        int hidden, float eps, cudaStream_t st) {
+    if (rows <= 0) return;
+    add_rmsnorm_kernel<<<rows, 256, 0, st>>>(x, part, w, xn, hidden, eps);
+}
+
+// ---- SiLU(gate) * up -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+silu_mul_kernel(PartIn gu, __nv_bfloat16* __restrict__ act, int inter) {
+    const int row = blockIdx.y;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= inter) return;
+    const float4 g = part_load4(gu, row, c);
+    const float4 u = part_load4(gu, row, inter + c);
+    auto f = [](float a, float b) { return a / (1.f + __expf(-a)) * b; };
+    uint2 o;
+    o.x = pack_bf16(f(g.x, u.x), f(g.y, u.y));
+    o.y = pack_bf16(f(g.z, u.z), f(g.w, u.w));
+    *reinterpret_cast<uint2*>(act + (size_t)row * inter + c) = o;
+}
+
+void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st) {
+    if (rows <= 0) return;
+    dim3 grid((inter / 4 + 255) / 256, rows);
+    silu_mul_kernel<<<grid, 256, 0, st>>>(gu, act, inter);
+}
+
+// ---- K6 RoPE + KV-cache append --------------------------------------------------------------------
+// head_dim = 128, HF "rotate_half" convention: pairs (i, i + 64), inv_freq_i = theta^(-i/64).
+__global__ void __launch_bounds__(256)
+rope_kv_kernel(RopeArgs a) {
+    const int row = blockIdx.x;
+    const int slot = a.slot[row];
+    if (slot < 0) return;
+    const int pos = a.pos[row];
+    const int n_q = a.n_heads * 64, n_k = a.n_kv_heads * 64;
+    const float l2t = log2f(a.theta);
+    // work items: q pairs, k pairs (2 elements each), then v copy (2 elements per item)
+    const int total = n_q + n_k + n_k;
+    for (int it = threadIdx.x; it < total; it += blockDim.x) {
+        if (it < n_q + n_k) {
+            const bool is_q = it < n_q;
+            const int j = is_q ? it : it - n_q;
+            const int head = j >> 6, i = j & 63;
+            const int col = (is_q ? 0 : a.n_heads * 128) + head * 128 + i;
+            float x0, x1;
+            if (a.qkv.is_bf16) {
+                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
+                x0 = __bfloat162float(r[col]);
+                x1 = __bfloat162float(r[col + 64]);
+            } else {
+                const float* r = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
+                x0 = r[col]; x1 = r[col + 64];
+                for (int z = 1; z < a.qkv.n_splits; ++z) {
+                    x0 += r[(size_t)z * a.qkv.split_stride + col];
+                    x1 += r[(size_t)z * a.qkv.split_stride + col + 64];
+                }
+            }
+            const float inv_freq = exp2f(-l2t * (float)i * (1.f / 64.f));
+            float sn, cs;
+            sincosf((float)pos * inv_freq, &sn, &cs);
+            const float y0 = x0 * cs - x1 * sn;
+            const float y1 = x1 * cs + x0 * sn;
+            if (is_q) {
+                __nv_bfloat16* q = a.q_out + (size_t)row * (a.n_heads * 128) + head * 128 + i;
+                q[0] = __float2bfloat16(y0);
+                q[64] = __float2bfloat16(y1);
+            } else {
+                __nv_bfloat16* k = a.k_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i;
+                k[0] = __float2bfloat16(y0);
+                k[64] = __float2bfloat16(y1);
+            }
+        } else {
+            const int j = it - n_q - n_k;            // [0, n_kv*64): 2 elements each
+            const int head = j >> 6, i2 = (j & 63) * 2;
+            const int col = (a.n_heads + a.n_kv_heads) * 128 + head * 128 + i2;
+            float v0, v1;
+            if (a.qkv.is_bf16) {
+                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
+                v0 = __bfloat162float(r[col]); v1 = __bfloat162float(r[col + 1]);
+            } else {
+                const float* r = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
+                v0 = r[col]; v1 = r[col + 1];
+                for (int z = 1; z < a.qkv.n_splits; ++z) {
+                    v0 += r[(size_t)z * a.qkv.split_stride + col];
+                    v1 += r[(size_t)z * a.qkv.split_stride + col + 1];
+                }
+            }
+            __nv_bfloat16* v = a.v_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i2;
+            *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
+        }
+    }
+}
+
+void launch_rope_kv(const RopeArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return;
+    rope_kv_kernel<<<a.rows, 256, 0, st>>>(a);
+}
+
+// ---- greedy argmax (lowest index wins ties) ------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+argmax_kernel(PartIn logits, int vocab, int32_t* __restrict__ out_tok, float* __restrict__ out_val,
+              const int32_t* __restrict__ row_active, int32_t* __restrict__ pos_inc) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    const int row = blockIdx.x;
+    if (row_active && row_active[row] < 0) return;
+    const float* r = reinterpret_cast<const float*>(logits.ptr) + (size_t)row * logits.ld;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    const int v4 = vocab & ~3;
+    for (int c = threadIdx.x * 4; c < v4; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(r + c);
+        if (v.x > best) { best = v.x; bi = c; }
+        if (v.y > best) { best = v.y; bi = c + 1; }
+        if (v.z > best) { best = v.z; bi = c + 2; }
+        if (v.w > best) { best = v.w; bi = c + 3; }
+    }
+    for (int c = v4 + threadIdx.x; c < vocab; c += blockDim.x) {
+        const float v = r[c];
+        if (v > best) { best = v; bi = c; }
+    }
+    auto better = [](float v, int i, float bv, int bi_) { return v > bv || (v == bv && i < bi_); };
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? s_v[lane] : -INFINITY;
+        bi = lane < nw ? s_i[lane] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            out_tok[row] = bi;
+            if (out_val) out_val[row] = best;
+            if (pos_inc) pos_inc[row] += 1;
+        }
+    }
+}
+
+void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
+                   const int32_t* row_active, int32_t* pos_inc, cudaStream_t st) {
+    if (rows <= 0) return;
+    argmax_kernel<<<rows, 1024, 0, st>>>(logits, vocab, out_tok, out_val, row_active, pos_inc);
+}
+
+}  // namespace rr

@@ -505,6 +505,12 @@ RR_API int rr_router_snapshot(rr_router* r, rr_deployment_state* out) {
     return RR_OK;
 }
 
+RR_API int rr_mt_seed_state(uint64_t seed, uint32_t* out625) {
+    if (!out625) return RR_INVALID_ARGUMENT;
+    mt_seed_like_cpython(seed, out625);
+    return RR_OK;
+}
+
 RR_API int rr_router_seed(rr_router* r, uint64_t seed) {
     if (!r) return RR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(r->mu);
