@@ -1,0 +1,150 @@
+"""Parity of the engine (prefill + decode through the C-ABI) against the generated-token oracle.
+
+Stated tolerance (north_star: "within a stated fp16 logit tolerance"): the engine rounds activations to
+bf16 at every GEMM input and keeps an fp32 residual; the oracle is fp32 on the same bf16 weights.
+Per position, with d = logit_engine - logit_oracle and s = std(oracle logits over the vocabulary):
+rms(d) <= TOL_RMS * s and max|d| <= TOL_MAX * s, TOL_RMS = 0.02, TOL_MAX = 0.08 for <= 4 layers
+(the 32-layer bound is stated in tests/test_full_model_gpu.py), and the engine's argmax equals the
+oracle's wherever the oracle's top-2 margin exceeds 2 * TOL_MAX * s."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "llama_tiny_golden.pt")
+TOL_RMS, TOL_MAX = 0.02, 0.08
+
+
+def _cmp(got, ref, what):
+    ref = ref.float().cpu()
+    got = torch.as_tensor(got).float().cpu()
+    std = ref.std().item()
+    d = got - ref
+    err, rms = d.abs().max().item(), d.pow(2).mean().sqrt().item()
+    assert torch.isfinite(got).all(), what
+    assert rms <= TOL_RMS * std and err <= TOL_MAX * std, (what, rms / std, err / std)
+    top2 = ref.topk(2).values
+    if (top2[0] - top2[1]).item() > 2 * TOL_MAX * std:
+        assert int(got.argmax()) == int(ref.argmax()), what
+    return rms / std
+
+
+def test_engine_matches_hf_golden_tiny():
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    g = torch.load(GOLD)
+    w = make_weights(SPECS["tiny"], seed=g["seed"], sigma=g["sigma"], device="cpu", norm_jitter=g["norm_jitter"])
+    chk = float(sum(t.float().abs().sum() for t in w.tensors()))
+    assert abs(chk - g["weight_checksum"]) < 1e-3 * g["weight_checksum"]
+    eng = Engine(w.to("cuda"), max_batch=8, ctx_max=512, max_prefill_tokens=1024, use_cuda_graph=False)
+    try:
+        prompts = g["prompts"]
+        slots = [3, 0, 7, 1, 5, 2]
+        first, logits = eng.prefill(prompts, slots, want_logits=True)
+        worst = 0.0
+        for i, p in enumerate(prompts):
+            worst = max(worst, _cmp(logits[i], g["logits"][i][0], f"prefill len={len(p)}"))
+        # teacher-forced decode: feed the oracle's tokens, compare each step's logits
+        steps = len(g["tokens"][0]) - 1
+        for j in range(steps):
+            toks = [g["tokens"][i][j] for i in range(len(prompts))]
+            pos = [len(p) + j for p in prompts]
+            nxt, lg = eng.decode_step(slots, toks, pos, want_logits=True)
+            for i in range(len(prompts)):
+                worst = max(worst, _cmp(lg[i], g["logits"][i][j + 1], f"decode step {j} seq {i}"))
+        print(f"\n[tiny vs HF golden] worst rms(dlogit)/std = {worst:.4f}")
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("spec_name,max_batch", [("small", 16), ("small", 64), ("llama-3-8b-2l", 64)])
+def test_engine_matches_oracle(spec_name, max_batch):
+    from oracle import llama_ref
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS[spec_name]
+    w = make_weights(spec, seed=3, sigma=0.03 if spec_name == "small" else 0.02, device="cuda", norm_jitter=0.1)
+    eng = Engine(w, max_batch=max_batch, ctx_max=640, max_prefill_tokens=2048, use_cuda_graph=False)
+    try:
+        g = torch.Generator().manual_seed(5)
+        lens = [3, 64, 129, 300, 512]
+        prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in lens]
+        slots = [max_batch - 1, 0, 5, 2, 9]
+        first, logits = eng.prefill(prompts, slots, want_logits=True)
+        refs = [llama_ref.forward_logits(w, p)[-1] for p in prompts]
+        worst = max(_cmp(logits[i], refs[i], f"prefill {spec_name} len={lens[i]}") for i in range(len(lens)))
+        # 3 free-running decode steps, checked teacher-forced against the oracle on the engine's own tokens
+        toks = [list(p) for p in prompts]
+        cur = [int(t) for t in first]
+        for j in range(3):
+            pos = [len(t) for t in toks]
+            for t, c in zip(toks, cur):
+                t.append(c)
+            nxt, lg = eng.decode_step(slots, cur, pos, want_logits=True)
+            for i in range(len(lens)):
+                ref = llama_ref.forward_logits(w, toks[i])[-1]
+                worst = max(worst, _cmp(lg[i], ref, f"decode {spec_name} step {j} seq {i}"))
+            cur = [int(t) for t in nxt]
+        print(f"\n[{spec_name} B={max_batch}] worst rms(dlogit)/std = {worst:.4f}")
+    finally:
+        eng.close()
+
+
+def test_serving_loop_equals_stepwise_and_is_deterministic():
+    """submit/wait (continuous batching, CUDA graph) must produce exactly the tokens of the
+    synchronous prefill + decode_step path (same kernels, same order of arithmetic)."""
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["small"]
+    w = make_weights(spec, seed=11, sigma=0.03, device="cuda", norm_jitter=0.1)
+    g = torch.Generator().manual_seed(9)
+    lens = [5, 40, 64, 100, 17, 256, 33, 8, 90, 300, 12, 64]
+    new = [4, 9, 1, 12, 7, 5, 16, 3, 2, 8, 10, 6]
+    prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in lens]
+    eng = Engine(w, max_batch=4, ctx_max=512, max_prefill_tokens=512, use_cuda_graph=True)   # forces queueing
+    try:
+        tickets = [eng.submit(p, m) for p, m in zip(prompts, new)]
+        recs = [eng.wait(t, timeout=120) for t in tickets]
+        assert all(r.status == 0 for r in recs)
+        assert [len(r.tokens) for r in recs] == new
+        assert all(r.t_submit <= r.t_first_token <= r.t_done for r in recs)
+        # second pass: identical tokens (deterministic kernels)
+        tickets = [eng.submit(p, m) for p, m in zip(prompts, new)]
+        recs2 = [eng.wait(t, timeout=120) for t in tickets]
+        assert [r.tokens for r in recs2] == [r.tokens for r in recs]
+        st = eng.stats()
+        assert st["kernel_launches"] > 0 and st["generated_tokens"] == 2 * sum(new)
+        # stepwise reference on the same engine
+        for i in [0, 3, 6, 9]:
+            first, _ = eng.prefill([prompts[i]], [2])
+            out = [int(first[0])]
+            pos = lens[i]
+            while len(out) < new[i]:
+                nxt, _ = eng.decode_step([2], [out[-1]], [pos])
+                out.append(int(nxt[0])); pos += 1
+            assert out == recs[i].tokens, i
+    finally:
+        eng.close()
+
+
+def test_run_batch_and_fault_injection():
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["tiny"]
+    w = make_weights(spec, seed=1, sigma=0.05, device="cuda")
+    eng = Engine(w, max_batch=8, ctx_max=256, max_prefill_tokens=512, fail_prob=0.5, fail_seed=42)
+    try:
+        n = 40
+        ids = np.random.RandomState(0).randint(0, spec.vocab, size=(n, 16)).astype(np.int32)
+        start = np.arange(0, n * 16 + 1, 16, dtype=np.int32)
+        recs, toks = eng.run_batch(ids.reshape(-1), start, 5)
+        failed = [r.status == 7 for r in recs]
+        assert 8 <= sum(failed) <= 32                      # Bernoulli(0.5), seeded
+        assert all(len(r.tokens) == (0 if f else 5) for r, f in zip(recs, failed))
+        recs2, _ = eng.run_batch(ids.reshape(-1), start, 5)
+        ok1 = [r.tokens for r in recs if r.status == 0]
+        assert len(ok1) > 0
+    finally:
+        eng.close()
