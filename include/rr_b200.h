@@ -42,6 +42,9 @@ const char* rr_version(void);
 const char* rr_strerror(int rc);
 /* Last CUDA error string seen by the library on this thread (diagnostics). */
 const char* rr_last_cuda_error(void);
+/* Programmatic dependent launch between the library's kernels (default on; env RR_NO_PDL=1 turns it
+ * off).  Returns the previous setting.  Must not change between capture and replay of an engine graph. */
+int rr_set_pdl(int enabled);
 
 /* ================================================================================================
  * 1. Router: admission + rpm/tpm bucket debit + backend pick + cooldown + fallback chain (K1).
@@ -160,7 +163,8 @@ int rr_op_argmax(const float* logits, int ld, int rows, int vocab, int32_t* out_
                  float* out_val, const int32_t* row_active, int32_t* pos_inc, void* stream);
 int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
                       const int32_t* slot, const int32_t* pos, int rows, int n_heads,
-                      int n_kv_heads, int ctx_max, float scale, int kv_splits, void* stream);
+                      int n_kv_heads, int ctx_max /* % 64 == 0 */, int n_slots, float scale,
+                      int kv_splits, void* stream);
 int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
                        const int32_t* seq_start, const int32_t* seq_slot, int n_seqs, int max_len,
                        int n_heads, int n_kv_heads, int ctx_max, float scale, void* stream);

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "rr_version": (C.c_char_p, []),
     "rr_strerror": (C.c_char_p, [C.c_int]),
     "rr_last_cuda_error": (C.c_char_p, []),
+    "rr_set_pdl": (C.c_int, [C.c_int]),
     "rr_router_create": (C.c_int, [C.POINTER(DeploymentDesc), C.c_int, C.c_int, c_i32p, c_i32p,
                                    C.POINTER(RouterSettings), C.c_uint64, C.c_int,
                                    C.POINTER(vp)]),
@@ -122,7 +123,7 @@ PROTOTYPES = {
     "rr_op_rope_kv": (C.c_int, [vp, C.c_int, C.c_int, C.c_longlong, C.c_int, vp, vp, vp, vp, vp,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "rr_op_argmax": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
-    "rr_op_decode_attn": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+    "rr_op_decode_attn": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_int, vp]),
     "rr_op_prefill_attn": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_float, vp]),

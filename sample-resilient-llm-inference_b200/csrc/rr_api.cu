@@ -6,7 +6,10 @@
 
 #define RR_API extern "C" __attribute__((visibility("default")))
 
+#include <stdlib.h>
+
 namespace rr {
+int g_use_pdl = getenv("RR_NO_PDL") ? 0 : 1;
 thread_local char g_last_cuda_error[256] = "";
 void note_cuda_error(cudaError_t e) {
     if (e != cudaSuccess) {
@@ -39,6 +42,12 @@ RR_API const char* rr_strerror(int rc) {
 }
 
 RR_API const char* rr_last_cuda_error(void) { return g_last_cuda_error; }
+
+RR_API int rr_set_pdl(int enabled) {
+    int old = g_use_pdl;
+    g_use_pdl = enabled ? 1 : 0;
+    return old;
+}
 
 // ---------------------------------------------------------------- tokenizer (K2)
 // Byte-level: id 1 = BOS, then 3 + byte value (0/1/2 reserved: pad/bos/eos), folded into the
@@ -114,7 +123,7 @@ RR_API int rr_op_rope_kv(const void* qkv, int is_bf16, int n_splits, long long s
     a.qkv = mk_part(qkv, is_bf16, n_splits, split_stride, ld);
     a.q_out = (__nv_bfloat16*)q_out; a.k_cache = (__nv_bfloat16*)k_cache; a.v_cache = (__nv_bfloat16*)v_cache;
     a.slot = slot; a.pos = pos; a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads;
-    a.ctx_max = ctx_max; a.theta = theta;
+    a.ctx_max = ctx_max; a.theta = theta; a.table = nullptr;
     launch_rope_kv(a, (cudaStream_t)stream);
     return check_last();
 }
@@ -129,8 +138,8 @@ RR_API int rr_op_argmax(const float* logits, int ld, int rows, int vocab, int32_
 
 RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
                              const int32_t* slot, const int32_t* pos, int rows, int n_heads,
-                             int n_kv_heads, int ctx_max, float scale, int kv_splits, void* stream) {
-    if (!q || !k_cache || !v_cache || !out || !slot || !pos) return RR_INVALID_ARGUMENT;
+                             int n_kv_heads, int ctx_max, int n_slots, float scale, int kv_splits, void* stream) {
+    if (!q || !k_cache || !v_cache || !out || !slot || !pos || n_slots < 1) return RR_INVALID_ARGUMENT;
     if (n_kv_heads <= 0 || n_heads % n_kv_heads) return RR_INVALID_ARGUMENT;
     const int G = n_heads / n_kv_heads;
     if (!(G == 1 || G == 2 || G == 4 || G == 8)) return RR_INVALID_ARGUMENT;
@@ -139,6 +148,7 @@ RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_c
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.slot = slot; a.pos = pos;
     a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
     a.kv_splits = kv_splits < 1 ? 1 : kv_splits; a.ws = nullptr;
+    { int rcm = decode_attn_make_maps(&a, n_slots); if (rcm != RR_OK) return rcm; }
     float* ws = nullptr;
     if (a.kv_splits > 1) {
         cudaError_t e = cudaMallocAsync(&ws, decode_attn_ws_bytes(rows, n_heads, a.kv_splits), (cudaStream_t)stream);

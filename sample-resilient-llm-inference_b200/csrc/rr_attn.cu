@@ -1,9 +1,6 @@
 // rr_attn.cu — attention over the slot-contiguous KV cache  [slot][kv_head][ctx_max][128] bf16.
 //
-//  * decode_attn (K8): one query token per row, GQA group of G query heads shares each KV head.
-//    HBM-bound (reads ctx * 512 B per (row, kv_head)); K/V tiles of 64 tokens are staged with
-//    cp.async (LDGSTS, 16 B, coalesced) into double-buffered shared memory; fp32 online softmax;
-//    optional split-KV with a combine pass for small batches.
+//  * decode attention (K8) lives in rr_attn_decode.cu.
 //  * prefill_attn (K7): causal flash attention, 64 query rows x one head per CTA, bf16
 //    mma.sync.m16n8k16 with ldmatrix from XOR-swizzled shared memory.  (<1% of prefill FLOPs at
 //    512-token prompts — SURVEY.md §8d; the dense contraction of the path, the projections,
@@ -11,258 +8,13 @@
 //
 // Replaces the remote bedrock:InvokeModel call (reference iam/policy.json:8).
 #include "rr_ptx.cuh"
+#include "rr_launch.cuh"
 #include "rr_kernels.h"
 
 namespace rr {
 
 constexpr int HD = 128;          // head_dim
-constexpr int DT = 64;           // tokens per tile
-constexpr int KS_STRIDE = 136;   // padded K row (bf16 elements): 272 B -> conflict-free 16 B reads
-constexpr int DEC_THREADS = 128;
-
-template <int G>
-struct DecSmem {
-    __nv_bfloat16 k[2][DT][KS_STRIDE];
-    __nv_bfloat16 v[2][DT][HD];
-    float q[G][HD];
-    float s_part[2][G][DT];
-    float p[DT][G];
-    float alpha[G];
-    float o_red[G][HD];
-};
-
-template <int G>
-__global__ void __launch_bounds__(DEC_THREADS)
-decode_attn_kernel(DecodeAttnArgs a) {
-    extern __shared__ __align__(16) uint8_t dec_smem_raw[];
-    DecSmem<G>& S = *reinterpret_cast<DecSmem<G>*>(dec_smem_raw);
-    const int kvh = blockIdx.x, row = blockIdx.y, split = blockIdx.z;
-    const int slot = a.slot[row];
-    if (slot < 0) return;
-    const int ctx = a.pos[row] + 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // token range of this split (multiples of DT)
-    const int n_tiles_all = (ctx + DT - 1) / DT;
-    const int tiles_per = (n_tiles_all + a.kv_splits - 1) / a.kv_splits;
-    const int tile0 = split * tiles_per;
-    const int tile1 = min(n_tiles_all, tile0 + tiles_per);
-
-    const __nv_bfloat16* kbase = a.k_cache + ((size_t)slot * a.n_kv_heads + kvh) * a.ctx_max * HD;
-    const __nv_bfloat16* vbase = a.v_cache + ((size_t)slot * a.n_kv_heads + kvh) * a.ctx_max * HD;
-
-    // q (G heads x 128) -> fp32 smem, pre-scaled by scale*log2(e)
-    const float qs = a.scale * 1.4426950408889634f;
-    for (int i = tid; i < G * HD; i += DEC_THREADS) {
-        const int g = i / HD, d = i % HD;
-        S.q[g][d] = __bfloat162float(a.q[(size_t)row * a.n_heads * HD + (kvh * G + g) * HD + d]) * qs;
-    }
-
-    auto issue_tile = [&](int tile, int buf) {
-        const int t0 = tile * DT;
-        // 64 rows x 256 B = 1024 x 16 B chunks for K, same for V; 128 threads -> 8 + 8 each
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = tid + i * DEC_THREADS;       // chunk id
-            const int r = c >> 4, cc = c & 15;
-            const bool ok = (t0 + r) < ctx;
-            const size_t goff = (size_t)(t0 + (ok ? r : 0)) * HD + cc * 8;
-            cp_async_16_zfill(&S.k[buf][r][cc * 8], kbase + goff, ok);
-            cp_async_16_zfill(&S.v[buf][r][cc * 8], vbase + goff, ok);
-        }
-        cp_async_commit();
-    };
-
-    float m_run = -INFINITY, l_run = 0.f;   // per warp: head g = warp (+4 for G = 8), lane-replicated
-    float m_run2 = -INFINITY, l_run2 = 0.f;
-    float acc[G][2];
-#pragma unroll
-    for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = 0.f;
-
-    if (tile0 < tile1) issue_tile(tile0, 0);
-    for (int tile = tile0; tile < tile1; ++tile) {
-        const int buf = (tile - tile0) & 1;
-        if (tile + 1 < tile1) {
-            issue_tile(tile + 1, buf ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-
-        // ---- QK^T: thread = (token, half of the head dim), all G heads
-        {
-            const int tok = tid & 63, half = tid >> 6;
-            float dot[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) dot[g] = 0.f;
-            const __nv_bfloat16* kr = &S.k[buf][tok][half * 64];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 kv = *reinterpret_cast<const uint4*>(kr + c * 8);
-                const float k0 = bf16_lo(kv.x), k1 = bf16_hi(kv.x), k2 = bf16_lo(kv.y), k3 = bf16_hi(kv.y);
-                const float k4 = bf16_lo(kv.z), k5 = bf16_hi(kv.z), k6 = bf16_lo(kv.w), k7 = bf16_hi(kv.w);
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float4 qa = *reinterpret_cast<const float4*>(&S.q[g][half * 64 + c * 8]);
-                    const float4 qb = *reinterpret_cast<const float4*>(&S.q[g][half * 64 + c * 8 + 4]);
-                    dot[g] += k0 * qa.x + k1 * qa.y + k2 * qa.z + k3 * qa.w + k4 * qb.x + k5 * qb.y +
-                              k6 * qb.z + k7 * qb.w;
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) S.s_part[half][g][tok] = dot[g];
-        }
-        __syncthreads();
-
-        // ---- online softmax: warp w owns head w (and w + 4 when G == 8)
-        {
-            const int t0 = tile * DT;
-#pragma unroll
-            for (int rep = 0; rep < (G + 3) / 4; ++rep) {
-                const int g = warp + rep * 4;
-                if (g < G) {
-                    float s0 = S.s_part[0][g][lane] + S.s_part[1][g][lane];
-                    float s1 = S.s_part[0][g][lane + 32] + S.s_part[1][g][lane + 32];
-                    if (t0 + lane >= ctx) s0 = -INFINITY;
-                    if (t0 + lane + 32 >= ctx) s1 = -INFINITY;
-                    float mx = fmaxf(s0, s1);
-                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    float& mr = rep ? m_run2 : m_run;
-                    float& lr = rep ? l_run2 : l_run;
-                    const float m_new = fmaxf(mr, mx);          // finite: tile has >= 1 valid token
-                    const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
-                    float ps = p0 + p1;
-                    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-                    const float al = exp2f(mr - m_new);          // 0 on the first tile (mr = -inf)
-                    lr = lr * al + ps;
-                    mr = m_new;
-                    S.p[lane][g] = p0;
-                    S.p[lane + 32][g] = p1;
-                    if (lane == 0) S.alpha[g] = al;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- P V: thread = (dim pair, token half)
-        {
-            const int dp = tid & 63, th = tid >> 6;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float al = S.alpha[g];
-                acc[g][0] *= al;
-                acc[g][1] *= al;
-            }
-#pragma unroll 8
-            for (int t = 0; t < 32; ++t) {
-                const int tok = th * 32 + t;
-                const uint32_t vv = *reinterpret_cast<const uint32_t*>(&S.v[buf][tok][dp * 2]);
-                const float v0 = bf16_lo(vv), v1 = bf16_hi(vv);
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float p = S.p[tok][g];
-                    acc[g][0] += p * v0;
-                    acc[g][1] += p * v1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- combine the two token halves, normalise, write
-    {
-        const int dp = tid & 63, th = tid >> 6;
-        if (th == 1) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                S.o_red[g][dp * 2] = acc[g][0];
-                S.o_red[g][dp * 2 + 1] = acc[g][1];
-            }
-        }
-        // publish per-head (m, l): warp g lane 0
-#pragma unroll
-        for (int rep = 0; rep < (G + 3) / 4; ++rep) {
-            const int g = warp + rep * 4;
-            if (g < G && lane == 0) {
-                S.s_part[0][g][0] = rep ? m_run2 : m_run;
-                S.s_part[0][g][1] = rep ? l_run2 : l_run;
-            }
-        }
-        __syncthreads();
-        if (th == 0) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float o0 = acc[g][0] + S.o_red[g][dp * 2];
-                const float o1 = acc[g][1] + S.o_red[g][dp * 2 + 1];
-                const float m = S.s_part[0][g][0], l = S.s_part[0][g][1];
-                const int head = kvh * G + g;
-                if (a.kv_splits == 1) {
-                    const float inv = l > 0.f ? 1.f / l : 0.f;
-                    *reinterpret_cast<uint32_t*>(a.out + (size_t)row * a.n_heads * HD + head * HD + dp * 2) =
-                        pack_bf16(o0 * inv, o1 * inv);
-                } else {
-                    float* w = a.ws + (((size_t)row * a.n_heads + head) * a.kv_splits + split) * (HD + 2);
-                    w[dp * 2] = o0;
-                    w[dp * 2 + 1] = o1;
-                    if (dp == 0) { w[HD] = m; w[HD + 1] = l; }
-                }
-            }
-        }
-    }
-}
-
-// combine split-KV partials: grid (n_heads, rows), 64 threads (dim pairs)
-__global__ void decode_attn_combine_kernel(DecodeAttnArgs a) {
-    const int head = blockIdx.x, row = blockIdx.y;
-    if (a.slot[row] < 0) return;
-    const float* w = a.ws + ((size_t)row * a.n_heads + head) * a.kv_splits * (HD + 2);
-    float m = -INFINITY;
-    for (int s = 0; s < a.kv_splits; ++s) m = fmaxf(m, w[s * (HD + 2) + HD]);
-    float l = 0.f, o0 = 0.f, o1 = 0.f;
-    const int dp = threadIdx.x;
-    for (int s = 0; s < a.kv_splits; ++s) {
-        const float* ws = w + s * (HD + 2);
-        const float ms = ws[HD];
-        if (ms == -INFINITY) continue;                // empty split
-        const float sc = exp2f(ms - m);
-        l += ws[HD + 1] * sc;
-        o0 += ws[dp * 2] * sc;
-        o1 += ws[dp * 2 + 1] * sc;
-    }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    *reinterpret_cast<uint32_t*>(a.out + (size_t)row * a.n_heads * HD + head * HD + dp * 2) =
-        pack_bf16(o0 * inv, o1 * inv);
-}
-
-size_t decode_attn_ws_bytes(int rows, int n_heads, int kv_splits) {
-    return kv_splits > 1 ? (size_t)rows * n_heads * kv_splits * (HD + 2) * sizeof(float) : 0;
-}
-
-template <int G>
-static void launch_dec(const DecodeAttnArgs& a, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(decode_attn_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(DecSmem<G>));
-        attr = true;
-    }
-    dim3 grid(a.n_kv_heads, a.rows, a.kv_splits);
-    decode_attn_kernel<G><<<grid, DEC_THREADS, sizeof(DecSmem<G>), st>>>(a);
-    if (a.kv_splits > 1) decode_attn_combine_kernel<<<dim3(a.n_heads, a.rows), 64, 0, st>>>(a);
-}
-
-void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st) {
-    if (a.rows <= 0) return;
-    const int G = a.n_heads / a.n_kv_heads;
-    switch (G) {
-        case 1: launch_dec<1>(a, st); break;
-        case 2: launch_dec<2>(a, st); break;
-        case 4: launch_dec<4>(a, st); break;
-        case 8: launch_dec<8>(a, st); break;
-        default: break;
-    }
-}
+constexpr int DT = 64;           // KV tokens per tile
 
 // =================================================================================================
 // Prefill: causal flash attention with mma.sync (bf16 in, fp32 accumulate).
@@ -296,6 +48,8 @@ prefill_attn_kernel(PrefillAttnArgs a) {
     uint8_t* sQ = pf_smem;                       // 64 x 256 B
     uint8_t* sK = pf_smem + 16384;               // 2 x 64 x 256 B
     uint8_t* sV = pf_smem + 16384 + 32768;       // 2 x 64 x 256 B
+    griddep_launch();
+    griddep_wait();
 
     const int seq = blockIdx.z, head = blockIdx.y;
     // heaviest (last) q tiles first
@@ -456,7 +210,7 @@ void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((a.max_len + PF_Q - 1) / PF_Q, a.n_heads, a.n_seqs);
-    prefill_attn_kernel<<<grid, PF_THREADS, smem, st>>>(a);
+    launch_pdl(prefill_attn_kernel, grid, dim3(PF_THREADS), (size_t)smem, st, a);
 }
 
 }  // namespace rr

@@ -3,10 +3,12 @@
 // greedy argmax (K11 tail).  All are row-parallel, 16-byte vectorised, fp32 math.
 // Each consumer reads the producing GEMM's output either as fp32 split-K partials
 // P[z][row][col] (decode orientation) or as one bf16 matrix (prefill orientation).
+// Every kernel is PDL-aware (rr_launch.cuh): constants may be touched before griddep_wait().
 //
 // Replaces (together with rr_gemm.cu / rr_attn.cu) the remote bedrock:InvokeModel call
 // (reference iam/policy.json:8; src/demo_cris.py:233-238).
 #include "rr_ptx.cuh"
+#include "rr_launch.cuh"
 #include "rr_kernels.h"
 
 namespace rr {
@@ -42,6 +44,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ---- K3 embedding gather -----------------------------------------------------------------------
 __global__ void embed_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                              float* __restrict__ x, int hidden, const int32_t* __restrict__ row_active) {
+    griddep_launch();
+    griddep_wait();
     const int row = blockIdx.x;
     if (row_active && row_active[row] < 0) return;
     const int id = ids[row];
@@ -59,48 +63,71 @@ __global__ void embed_kernel(const int32_t* __restrict__ ids, const __nv_bfloat1
 void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int rows, int hidden,
                   const int32_t* row_active, cudaStream_t st) {
     if (rows <= 0) return;
-    embed_kernel<<<rows, 256, 0, st>>>(ids, table, x, hidden, row_active);
+    launch_pdl(embed_kernel, dim3(rows), dim3(256), 0, st, ids, table, x, hidden, row_active);
 }
 
 // ---- K4 residual add + RMSNorm (+ split-K reduce) ------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One CTA per row; the row (hidden <= 8192) stays in registers between the sum-of-squares pass and
+// the normalise pass: x and the split planes are read exactly once.
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_MAXV = 8;      // float4 per thread -> hidden <= 8192
+
+__global__ void __launch_bounds__(NORM_THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
                    __nv_bfloat16* __restrict__ xn, int hidden, float eps) {
     __shared__ float red[32];
+    griddep_launch();
     const int row = blockIdx.x;
     float* xr = x + (size_t)row * hidden;
+    // norm weights are constants: fetch them before waiting for the producer
+    uint2 wv[NORM_MAXV];
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+        if (c < hidden) wv[i] = *reinterpret_cast<const uint2*>(w + c);
+    }
+    griddep_wait();
+    float4 v[NORM_MAXV];
     float ss = 0.f;
-    for (int c = threadIdx.x * 4; c < hidden; c += blockDim.x * 4) {
-        float4 v = *reinterpret_cast<float4*>(xr + c);
-        if (part.ptr) {
-            const float4 p = part_load4(part, row, c);
-            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-            *reinterpret_cast<float4*>(xr + c) = v;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+        if (c < hidden) {
+            v[i] = *reinterpret_cast<float4*>(xr + c);
+            if (part.ptr) {
+                const float4 p = part_load4(part, row, c);
+                v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+                *reinterpret_cast<float4*>(xr + c) = v[i];
+            }
+            ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
         }
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     ss = block_sum(ss, red);
     const float inv = rsqrtf(ss / (float)hidden + eps);
     __nv_bfloat16* out = xn + (size_t)row * hidden;
-    for (int c = threadIdx.x * 4; c < hidden; c += blockDim.x * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + c);   // own writes: L1/L2 hit
-        const uint2 wv = *reinterpret_cast<const uint2*>(w + c);
-        uint2 o;
-        o.x = pack_bf16(v.x * inv * bf16_lo(wv.x), v.y * inv * bf16_hi(wv.x));
-        o.y = pack_bf16(v.z * inv * bf16_lo(wv.y), v.w * inv * bf16_hi(wv.y));
-        *reinterpret_cast<uint2*>(out + c) = o;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+        if (c < hidden) {
+            uint2 o;
+            o.x = pack_bf16(v[i].x * inv * bf16_lo(wv[i].x), v[i].y * inv * bf16_hi(wv[i].x));
+            o.y = pack_bf16(v[i].z * inv * bf16_lo(wv[i].y), v[i].w * inv * bf16_hi(wv[i].y));
+            *reinterpret_cast<uint2*>(out + c) = o;
+        }
     }
 }
 
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
                         int hidden, float eps, cudaStream_t st) {
-    if (rows <= 0) return;
-    add_rmsnorm_kernel<<<rows, 256, 0, st>>>(x, part, w, xn, hidden, eps);
+    if (rows <= 0 || hidden > NORM_THREADS * 4 * NORM_MAXV) return;
+    launch_pdl(add_rmsnorm_kernel, dim3(rows), dim3(NORM_THREADS), 0, st, x, part, w, xn, hidden, eps);
 }
 
 // ---- SiLU(gate) * up -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(PartIn gu, __nv_bfloat16* __restrict__ act, int inter) {
+    griddep_launch();
+    griddep_wait();
     const int row = blockIdx.y;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c >= inter) return;
@@ -116,79 +143,95 @@ silu_mul_kernel(PartIn gu, __nv_bfloat16* __restrict__ act, int inter) {
 void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st) {
     if (rows <= 0) return;
     dim3 grid((inter / 4 + 255) / 256, rows);
-    silu_mul_kernel<<<grid, 256, 0, st>>>(gu, act, inter);
+    launch_pdl(silu_mul_kernel, grid, dim3(256), 0, st, gu, act, inter);
 }
 
 // ---- K6 RoPE + KV-cache append --------------------------------------------------------------------
 // head_dim = 128, HF "rotate_half" convention: pairs (i, i + 64), inv_freq_i = theta^(-i/64).
+// cos/sin come from a table [ctx_max][64] (float2) built once per engine in double precision;
+// without a table (kernel-level tests) they are computed inline.
+__global__ void rope_table_kernel(float2* __restrict__ table, int ctx_max, double theta) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ctx_max * 64) return;
+    const int pos = idx >> 6, i = idx & 63;
+    const double inv_freq = pow(theta, -(double)i / 64.0);
+    // the oracle (and HF) form the angle in fp32: pos * float(inv_freq)
+    const float ang = (float)pos * (float)inv_freq;
+    table[idx] = make_float2((float)cos((double)ang), (float)sin((double)ang));
+}
+
+void launch_rope_table(float2* table, int ctx_max, float theta, cudaStream_t st) {
+    const int n = ctx_max * 64;
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, ctx_max, (double)theta);
+}
+
+__device__ __forceinline__ float2 part_load2(const PartIn& p, int row, int col) {   // 2 consecutive columns
+    if (p.is_bf16) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(
+            reinterpret_cast<const __nv_bfloat16*>(p.ptr) + (size_t)row * p.ld + col);
+        return make_float2(bf16_lo(v), bf16_hi(v));
+    }
+    const float* base = reinterpret_cast<const float*>(p.ptr) + (size_t)row * p.ld + col;
+    float2 acc = *reinterpret_cast<const float2*>(base);
+    for (int z = 1; z < p.n_splits; ++z) {
+        const float2 t = *reinterpret_cast<const float2*>(base + (size_t)z * p.split_stride);
+        acc.x += t.x; acc.y += t.y;
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(256)
 rope_kv_kernel(RopeArgs a) {
+    griddep_launch();
+    griddep_wait();
     const int row = blockIdx.x;
     const int slot = a.slot[row];
     if (slot < 0) return;
     const int pos = a.pos[row];
-    const int n_q = a.n_heads * 64, n_k = a.n_kv_heads * 64;
-    const float l2t = log2f(a.theta);
-    // work items: q pairs, k pairs (2 elements each), then v copy (2 elements per item)
+    // work items of 2 rotation pairs: (head, i..i+1) for q heads then k heads, then v copies (4 elements)
+    const int n_q = a.n_heads * 32, n_k = a.n_kv_heads * 32;
     const int total = n_q + n_k + n_k;
+    const float l2t = a.table ? 0.f : log2f(a.theta);
     for (int it = threadIdx.x; it < total; it += blockDim.x) {
         if (it < n_q + n_k) {
             const bool is_q = it < n_q;
             const int j = is_q ? it : it - n_q;
-            const int head = j >> 6, i = j & 63;
+            const int head = j >> 5, i = (j & 31) * 2;
             const int col = (is_q ? 0 : a.n_heads * 128) + head * 128 + i;
-            float x0, x1;
-            if (a.qkv.is_bf16) {
-                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
-                x0 = __bfloat162float(r[col]);
-                x1 = __bfloat162float(r[col + 64]);
+            const float2 lo = part_load2(a.qkv, row, col);
+            const float2 hi = part_load2(a.qkv, row, col + 64);
+            float c0, s0, c1, s1;
+            if (a.table) {
+                const float4 t = *reinterpret_cast<const float4*>(a.table + (size_t)pos * 64 + i);
+                c0 = t.x; s0 = t.y; c1 = t.z; s1 = t.w;
             } else {
-                const float* r = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
-                x0 = r[col]; x1 = r[col + 64];
-                for (int z = 1; z < a.qkv.n_splits; ++z) {
-                    x0 += r[(size_t)z * a.qkv.split_stride + col];
-                    x1 += r[(size_t)z * a.qkv.split_stride + col + 64];
-                }
+                sincosf((float)pos * exp2f(-l2t * (float)i * (1.f / 64.f)), &s0, &c0);
+                sincosf((float)pos * exp2f(-l2t * (float)(i + 1) * (1.f / 64.f)), &s1, &c1);
             }
-            const float inv_freq = exp2f(-l2t * (float)i * (1.f / 64.f));
-            float sn, cs;
-            sincosf((float)pos * inv_freq, &sn, &cs);
-            const float y0 = x0 * cs - x1 * sn;
-            const float y1 = x1 * cs + x0 * sn;
-            if (is_q) {
-                __nv_bfloat16* q = a.q_out + (size_t)row * (a.n_heads * 128) + head * 128 + i;
-                q[0] = __float2bfloat16(y0);
-                q[64] = __float2bfloat16(y1);
-            } else {
-                __nv_bfloat16* k = a.k_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i;
-                k[0] = __float2bfloat16(y0);
-                k[64] = __float2bfloat16(y1);
-            }
+            const uint32_t o_lo = pack_bf16(lo.x * c0 - hi.x * s0, lo.y * c1 - hi.y * s1);
+            const uint32_t o_hi = pack_bf16(hi.x * c0 + lo.x * s0, hi.y * c1 + lo.y * s1);
+            __nv_bfloat16* dst = is_q
+                ? a.q_out + (size_t)row * (a.n_heads * 128) + head * 128 + i
+                : a.k_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i;
+            *reinterpret_cast<uint32_t*>(dst) = o_lo;
+            *reinterpret_cast<uint32_t*>(dst + 64) = o_hi;
         } else {
-            const int j = it - n_q - n_k;            // [0, n_kv*64): 2 elements each
-            const int head = j >> 6, i2 = (j & 63) * 2;
-            const int col = (a.n_heads + a.n_kv_heads) * 128 + head * 128 + i2;
-            float v0, v1;
-            if (a.qkv.is_bf16) {
-                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
-                v0 = __bfloat162float(r[col]); v1 = __bfloat162float(r[col + 1]);
-            } else {
-                const float* r = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)row * a.qkv.ld;
-                v0 = r[col]; v1 = r[col + 1];
-                for (int z = 1; z < a.qkv.n_splits; ++z) {
-                    v0 += r[(size_t)z * a.qkv.split_stride + col];
-                    v1 += r[(size_t)z * a.qkv.split_stride + col + 1];
-                }
-            }
-            __nv_bfloat16* v = a.v_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i2;
-            *reinterpret_cast<uint32_t*>(v) = pack_bf16(v0, v1);
+            const int j = it - n_q - n_k;            // [0, n_kv*32): 4 elements each
+            const int head = j >> 5, i4 = (j & 31) * 4;
+            const int col = (a.n_heads + a.n_kv_heads) * 128 + head * 128 + i4;
+            const float4 v = part_load4(a.qkv, row, col);
+            __nv_bfloat16* dst = a.v_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i4;
+            uint2 o;
+            o.x = pack_bf16(v.x, v.y);
+            o.y = pack_bf16(v.z, v.w);
+            *reinterpret_cast<uint2*>(dst) = o;
         }
     }
 }
 
 void launch_rope_kv(const RopeArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return;
-    rope_kv_kernel<<<a.rows, 256, 0, st>>>(a);
+    launch_pdl(rope_kv_kernel, dim3(a.rows), dim3(256), 0, st, a);
 }
 
 // ---- greedy argmax (lowest index wins ties) ------------------------------------------------------
@@ -197,6 +240,8 @@ argmax_kernel(PartIn logits, int vocab, int32_t* __restrict__ out_tok, float* __
               const int32_t* __restrict__ row_active, int32_t* __restrict__ pos_inc) {
     __shared__ float s_v[32];
     __shared__ int s_i[32];
+    griddep_launch();
+    griddep_wait();
     const int row = blockIdx.x;
     if (row_active && row_active[row] < 0) return;
     const float* r = reinterpret_cast<const float*>(logits.ptr) + (size_t)row * logits.ld;
@@ -243,7 +288,7 @@ argmax_kernel(PartIn logits, int vocab, int32_t* __restrict__ out_tok, float* __
 void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
                    const int32_t* row_active, int32_t* pos_inc, cudaStream_t st) {
     if (rows <= 0) return;
-    argmax_kernel<<<rows, 1024, 0, st>>>(logits, vocab, out_tok, out_val, row_active, pos_inc);
+    launch_pdl(argmax_kernel, dim3(rows), dim3(1024), 0, st, logits, vocab, out_tok, out_val, row_active, pos_inc);
 }
 
 }  // namespace rr

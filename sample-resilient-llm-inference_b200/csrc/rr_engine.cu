@@ -13,6 +13,7 @@
 // and replayed; per-row metadata (token, position, active flag) lives on the device so replays
 // need no parameter changes.
 #include "rr_kernels.h"
+#include "rr_launch.cuh"
 
 #include <atomic>
 #include <chrono>
@@ -33,6 +34,8 @@ void note_cuda_error(cudaError_t e);
 
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dst, int hidden) {
+    griddep_launch();
+    griddep_wait();
     const int r = blockIdx.x;
     const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)idx[r] * hidden);
     uint4* d = reinterpret_cast<uint4*>(dst + (size_t)r * hidden);
@@ -43,6 +46,8 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 __global__ void activate_rows_kernel(const int32_t* __restrict__ seq_slot, const int32_t* __restrict__ first_tok,
                                      const int32_t* __restrict__ seq_start, int n, int32_t* __restrict__ d_tok,
                                      int32_t* __restrict__ d_pos, int32_t* __restrict__ d_slot) {
+    griddep_launch();
+    griddep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = seq_slot[i];
@@ -90,10 +95,12 @@ struct rr_engine {
     float* x;
     __nv_bfloat16 *xn, *qbuf, *attn_out, *act;
     float *part, *logits, *attn_ws;
+    float2* rope_table;
     __nv_bfloat16 *kcache, *vcache;
     size_t kv_layer_stride;
     int kv_splits;
     std::vector<GemmPlan> pl_qkv, pl_o, pl_gu, pl_down;
+    std::vector<DecodeAttnArgs> attn_args;   // per layer (TMA maps of that layer's K / V cache)
     GemmPlan pl_head, pl_head_pf;
     int s_qkv, s_o, s_gu, s_down;
     cudaGraphExec_t graph = nullptr;
@@ -186,14 +193,9 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
         ra.qkv = part_f32(e->part, e->s_qkv, B, e->nqkv);
         ra.q_out = e->qbuf; ra.k_cache = kc; ra.v_cache = vc; ra.slot = e->d_slot; ra.pos = e->d_pos;
         ra.rows = B; ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max;
-        ra.theta = d.rope_theta;
+        ra.theta = d.rope_theta; ra.table = e->rope_table;
         launch_rope_kv(ra, s); ++nl;
-        DecodeAttnArgs da;
-        da.q = e->qbuf; da.k_cache = kc; da.v_cache = vc; da.out = e->attn_out; da.slot = e->d_slot;
-        da.pos = e->d_pos; da.rows = B; da.n_heads = d.n_heads; da.n_kv_heads = d.n_kv_heads;
-        da.ctx_max = e->o.ctx_max; da.scale = 1.0f / sqrtf((float)d.head_dim); da.ws = e->attn_ws;
-        da.kv_splits = e->kv_splits;
-        launch_decode_attn(da, s); nl += e->kv_splits > 1 ? 2 : 1;
+        launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
         if (gemm_launch(e->pl_o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         launch_add_rmsnorm(e->x, part_f32(e->part, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
                            e->xn, B, d.hidden, d.rms_eps, s); ++nl;
@@ -312,6 +314,7 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         ra.qkv = part_bf16(e->pqkv, e->nqkv);
         ra.q_out = e->pq; ra.k_cache = kc; ra.v_cache = vc; ra.slot = p_slt; ra.pos = p_pos; ra.rows = T;
         ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max; ra.theta = d.rope_theta;
+        ra.table = e->rope_table;
         launch_rope_kv(ra, s); ++nl;
         PrefillAttnArgs pa;
         pa.q = e->pq; pa.k_cache = kc; pa.v_cache = vc; pa.out = e->pattn; pa.seq_start = p_ss; pa.seq_slot = p_sl;
@@ -328,11 +331,12 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)nw, e->pxn, T, d.hidden,
                            d.rms_eps, s); ++nl;
     }
-    gather_rows_kernel<<<n_seqs, 256, 0, s>>>(e->pxn, p_last, e->xn_last, d.hidden); ++nl;
+    launch_pdl(gather_rows_kernel, dim3(n_seqs), dim3(256), 0, s, (const __nv_bfloat16*)e->pxn, (const int32_t*)p_last,
+               e->xn_last, d.hidden); ++nl;
     if (gemm_launch(e->pl_head_pf, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
     launch_argmax(part_f32(e->logits, 1, e->Bm, d.vocab), n_seqs, d.vocab, e->p_first, nullptr, nullptr, nullptr, s); ++nl;
-    activate_rows_kernel<<<(n_seqs + 127) / 128, 128, 0, s>>>(p_sl, e->p_first, p_ss, n_seqs, e->d_tok, e->d_pos,
-                                                             e->d_slot); ++nl;
+    launch_pdl(activate_rows_kernel, dim3((n_seqs + 127) / 128), dim3(128), 0, s, (const int32_t*)p_sl,
+               (const int32_t*)e->p_first, (const int32_t*)p_ss, n_seqs, e->d_tok, e->d_pos, e->d_slot); ++nl;
     CK(cudaMemcpyAsync(e->h_tok, e->p_first, sizeof(int32_t) * n_seqs, cudaMemcpyDeviceToHost, s));
     e->st.d2h_bytes += sizeof(int32_t) * n_seqs;
     if (logits_host) {
@@ -469,7 +473,8 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         return RR_INVALID_ARGUMENT;
     const int G = d.n_heads / d.n_kv_heads;
     if (!(G == 1 || G == 2 || G == 4 || G == 8)) return RR_INVALID_ARGUMENT;
-    if (opts->max_batch < 1 || opts->max_batch > 256 || opts->ctx_max < 2) return RR_INVALID_ARGUMENT;
+    if (opts->max_batch < 1 || opts->max_batch > 256 || opts->ctx_max < 64 || opts->ctx_max % 64)
+        return RR_INVALID_ARGUMENT;
     CK(cudaSetDevice(opts->device));
     rr_engine* e = new (std::nothrow) rr_engine();
     if (!e) return RR_INTERNAL;
@@ -509,6 +514,8 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRY(dalloc(e, &e->part, part_elems));
     TRY(dalloc(e, &e->logits, (size_t)B * d.vocab));
     TRY(dalloc(e, &e->xn_last, (size_t)B * d.hidden));
+    TRY(dalloc(e, &e->rope_table, (size_t)opts->ctx_max * 64));
+    launch_rope_table(e->rope_table, opts->ctx_max, d.rope_theta, e->stream);
     e->kv_layer_stride = (size_t)B * d.n_kv_heads * opts->ctx_max * 128;
     TRY(dalloc(e, &e->kcache, e->kv_layer_stride * L));
     TRY(dalloc(e, &e->vcache, e->kv_layer_stride * L));
@@ -536,7 +543,15 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRYC(cudaMallocHost(&e->h_tok, sizeof(int32_t) * (B > 16 ? B : 16)));
 
     e->pl_qkv.resize(L); e->pl_o.resize(L); e->pl_gu.resize(L); e->pl_down.resize(L);
+    e->attn_args.resize(L);
     for (int l = 0; l < L; ++l) {
+        DecodeAttnArgs& da = e->attn_args[l];
+        da.q = e->qbuf; da.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
+        da.v_cache = e->vcache + (size_t)l * e->kv_layer_stride; da.out = e->attn_out; da.slot = e->d_slot;
+        da.pos = e->d_pos; da.rows = B; da.n_heads = d.n_heads; da.n_kv_heads = d.n_kv_heads;
+        da.ctx_max = opts->ctx_max; da.scale = 1.0f / sqrtf((float)d.head_dim); da.ws = e->attn_ws;
+        da.kv_splits = e->kv_splits;
+        TRY(decode_attn_make_maps(&da, B));
         TRY(gemm_plan_init(&e->pl_qkv[l], e->wqkv[l], e->nqkv, d.hidden, e->xn, B, d.hidden, d.hidden, e->part,
                            e->nqkv, B, e->s_qkv, OUT_TRANSPOSED_F32, e->bn_dec));
         TRY(gemm_plan_init(&e->pl_o[l], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->nq, e->nq, e->part, d.hidden,

@@ -15,6 +15,7 @@
 // Replaces: the remote bedrock:InvokeModel call (reference iam/policy.json:8,
 // src/demo_cris.py:233-238) — there is no reference kernel; see DESIGN.md §kernels.
 #include "rr_ptx.cuh"
+#include "rr_launch.cuh"
 #include "rr_kernels.h"
 
 #include <mutex>
@@ -79,6 +80,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    griddep_launch();   // PDL: the next kernel may start its prologue now
 
     const int tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
     const int tilesB = (rowsB + BN - 1) / BN;
@@ -119,10 +121,47 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t polB = l2_policy_evict_last();
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+            // PDL prefetch: the weight operand is constant, so the first kStages tiles of it are
+            // requested BEFORE waiting for the preceding kernel; only the activation operand waits.
+            // (decode: A = weights; prefill: B = weights.)
+            int pre = 0;
+            if (blockIdx.x < n_work) {
+                const TileCoord t = decode_work(blockIdx.x, tilesA, tilesB, splits);
                 const int kb0 = (int)(((long long)kblocks * t.z) / splits);
                 const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
+                pre = min(kStages, kb1 - kb0);
+                for (int i = 0; i < pre; ++i) {
+                    mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+                    if (MODE == OUT_TRANSPOSED_F32)
+                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (kb0 + i) * BLOCK_K,
+                                         t.a_tile * BLOCK_A, polA);
+                    else
+                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (kb0 + i) * BLOCK_K,
+                                         t.b_tile * BN, polB);
+                }
+                // (An L2 prefetch of the rest of the weight panel here was measured SLOWER on B200:
+                //  5.12 -> 5.37 ms per decode step; the 8 in-flight stages are the whole head start.)
+                griddep_wait();
+                for (int i = 0; i < pre; ++i) {
+                    if (MODE == OUT_TRANSPOSED_F32)
+                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (kb0 + i) * BLOCK_K,
+                                         t.b_tile * BN, polB);
+                    else
+                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (kb0 + i) * BLOCK_K,
+                                         t.a_tile * BLOCK_A, polA);
+                }
+            }
+            bool first = true;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+                int kb0 = (int)(((long long)kblocks * t.z) / splits);
+                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
+                if (first) {                       // the first `pre` k-blocks are already in flight
+                    first = false;
+                    kb0 += pre;
+                    stage = pre % kStages;
+                    phase = (pre == kStages) ? 1u : 0u;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -180,6 +219,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
         int it = 0;
+        griddep_wait();                               // `out` may still be read by the preceding kernel
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             const TileCoord t = decode_work(w, tilesA, tilesB, splits);
             const int acc = it & 1;
@@ -305,9 +345,9 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
     const int n_work = tilesA * tilesB * p.splits;
     int grid = n_work < num_sms() ? n_work : num_sms();
     if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
-    kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(p.tmA, p.tmB, p.out, p.rowsA, p.rowsB, p.K,
-                                                      p.splits, p.ldo, p.ld_rows);
-    return cudaGetLastError() == cudaSuccess ? RR_OK : RR_ERR_CUDA;
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::kSmemBytes, st, p.tmA, p.tmB,
+                                p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows);
+    return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,

@@ -55,8 +55,10 @@ struct RopeArgs {
     const int32_t* pos;       // per row: position
     int rows, n_heads, n_kv_heads, ctx_max;
     float theta;
+    const float2* table;      // [ctx_max][64] (cos, sin) or null: compute inline
 };
 void launch_rope_kv(const RopeArgs& a, cudaStream_t st);
+void launch_rope_table(float2* table, int ctx_max, float theta, cudaStream_t st);
 // argmax over fp32 logits [rows, vocab] (partials with n_splits = 1); writes next token, and if
 // advance != 0: pos[row]++ (decode bookkeeping folded into the same launch).
 void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
@@ -74,7 +76,9 @@ struct DecodeAttnArgs {
     float scale;
     float* ws;                // split-KV workspace (may be null when kv_splits == 1)
     int kv_splits;
+    CUtensorMap tmK, tmV;     // [n_slots*n_kv_heads*ctx_max, 128] views of the caches, box {64, 64}, SW128
 };
+int decode_attn_make_maps(DecodeAttnArgs* a, int n_slots);   // fills tmK / tmV (ctx_max % 64 == 0)
 void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st);
 size_t decode_attn_ws_bytes(int rows, int n_heads, int kv_splits);
 

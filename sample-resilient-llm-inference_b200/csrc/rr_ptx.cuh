@@ -97,6 +97,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// L2 prefetch of one tile (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

@@ -140,7 +140,7 @@ def _attn_ref(q, k, v, scale):
 def test_decode_attention(H, KV, splits):
     lib = L()
     g = torch.Generator(device=DEV).manual_seed(H + KV + splits)
-    rows, ctx_max, slots = 11, 700, 12
+    rows, ctx_max, slots = 11, 704, 12
     kc = torch.randn(slots, KV, ctx_max, 128, device=DEV, generator=g).bfloat16()
     vc = torch.randn(slots, KV, ctx_max, 128, device=DEV, generator=g).bfloat16()
     q = torch.randn(rows, H * 128, device=DEV, generator=g).bfloat16()
@@ -148,7 +148,7 @@ def test_decode_attention(H, KV, splits):
     pos = torch.tensor([0, 5, 63, 64, 65, 127, 128, 300, 511, 639, 699], device=DEV, dtype=torch.int32)
     out = torch.zeros(rows, H * 128, device=DEV, dtype=torch.bfloat16)
     scale = 1 / math.sqrt(128)
-    lib.check(lib.lib.rr_op_decode_attn(P(q), P(kc), P(vc), P(out), P(slot), P(pos), rows, H, KV, ctx_max, scale, splits, None))
+    lib.check(lib.lib.rr_op_decode_attn(P(q), P(kc), P(vc), P(out), P(slot), P(pos), rows, H, KV, ctx_max, slots, scale, splits, None))
     torch.cuda.synchronize()
     for r in range(rows):
         if slot[r] < 0:
