@@ -72,6 +72,8 @@ RR_API int rr_tokenize(const uint8_t* text, size_t n_bytes, int32_t vocab, int32
 }
 
 // ---------------------------------------------------------------- kernels
+RR_API int rr_gemm_streamk_planes(int rowsA, int K) { return gemm_streamk_planes(rowsA, K); }
+
 RR_API int rr_gemm_bf16(const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB, int K,
                         void* out, int ldo, int ld_rows, int splits, int mode, int bn,
                         void* stream) {

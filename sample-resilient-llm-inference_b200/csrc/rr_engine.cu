@@ -94,7 +94,7 @@ struct rr_engine {
     int32_t *d_tok, *d_pos, *d_slot;
     float* x;
     __nv_bfloat16 *xn, *qbuf, *attn_out, *act;
-    float *part, *logits, *attn_ws;
+    float *part_qkv, *part_o, *part_gu, *part_down, *logits, *attn_ws;   // stream-K partial planes (zeroed once)
     float2* rope_table;
     __nv_bfloat16 *kcache, *vcache;
     size_t kv_layer_stride;
@@ -190,20 +190,20 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
         __nv_bfloat16* vc = e->vcache + (size_t)l * e->kv_layer_stride;
         if (gemm_launch(e->pl_qkv[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         RopeArgs ra;
-        ra.qkv = part_f32(e->part, e->s_qkv, B, e->nqkv);
+        ra.qkv = part_f32(e->part_qkv, e->s_qkv, B, e->nqkv);
         ra.q_out = e->qbuf; ra.k_cache = kc; ra.v_cache = vc; ra.slot = e->d_slot; ra.pos = e->d_pos;
         ra.rows = B; ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max;
         ra.theta = d.rope_theta; ra.table = e->rope_table;
         launch_rope_kv(ra, s); ++nl;
         launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
         if (gemm_launch(e->pl_o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        launch_add_rmsnorm(e->x, part_f32(e->part, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
+        launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
                            e->xn, B, d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(e->pl_gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        launch_silu_mul(part_f32(e->part, e->s_gu, B, 2 * d.inter), e->act, B, d.inter, s); ++nl;
+        launch_silu_mul(part_f32(e->part_gu, e->s_gu, B, 2 * d.inter), e->act, B, d.inter, s); ++nl;
         if (gemm_launch(e->pl_down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         const void* nw = (l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm;
-        launch_add_rmsnorm(e->x, part_f32(e->part, e->s_down, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
+        launch_add_rmsnorm(e->x, part_f32(e->part_down, e->s_down, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
                            d.hidden, d.rms_eps, s); ++nl;
     }
     if (gemm_launch(e->pl_head, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
@@ -499,11 +499,10 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRYC(cudaEventCreate(&e->ev0));
     TRYC(cudaEventCreate(&e->ev1));
     const int B = e->Bm;
+    // Uniform split-K planes.  (stream-K — gemm_plan_init(splits = 0) — was measured on B200: it only helps
+    // gate/up by 5 % and costs extra planes for the consumers: 4.55 -> 4.92 ms per decode step.)
     e->s_qkv = pick_splits(e->nqkv, d.hidden); e->s_o = pick_splits(d.hidden, e->nq);
     e->s_gu = pick_splits(2 * d.inter, d.hidden); e->s_down = pick_splits(d.hidden, d.inter);
-    size_t part_elems = 0;
-    auto upd = [&](int s, int n) { size_t v = (size_t)s * B * n; if (v > part_elems) part_elems = v; };
-    upd(e->s_qkv, e->nqkv); upd(e->s_o, d.hidden); upd(e->s_gu, 2 * d.inter); upd(e->s_down, d.hidden);
     TRY(dalloc(e, &e->d_tok, B)); TRY(dalloc(e, &e->d_pos, B)); TRY(dalloc(e, &e->d_slot, B));
     TRYC(cudaMemset(e->d_slot, 0xff, sizeof(int32_t) * B));
     TRY(dalloc(e, &e->x, (size_t)B * d.hidden));
@@ -511,7 +510,10 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRY(dalloc(e, &e->qbuf, (size_t)B * e->nq));
     TRY(dalloc(e, &e->attn_out, (size_t)B * e->nq));
     TRY(dalloc(e, &e->act, (size_t)B * d.inter));
-    TRY(dalloc(e, &e->part, part_elems));
+    TRY(dalloc(e, &e->part_qkv, (size_t)e->s_qkv * B * e->nqkv));
+    TRY(dalloc(e, &e->part_o, (size_t)e->s_o * B * d.hidden));
+    TRY(dalloc(e, &e->part_gu, (size_t)e->s_gu * B * 2 * d.inter));
+    TRY(dalloc(e, &e->part_down, (size_t)e->s_down * B * d.hidden));
     TRY(dalloc(e, &e->logits, (size_t)B * d.vocab));
     TRY(dalloc(e, &e->xn_last, (size_t)B * d.hidden));
     TRY(dalloc(e, &e->rope_table, (size_t)opts->ctx_max * 64));
@@ -552,13 +554,13 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         da.ctx_max = opts->ctx_max; da.scale = 1.0f / sqrtf((float)d.head_dim); da.ws = e->attn_ws;
         da.kv_splits = e->kv_splits;
         TRY(decode_attn_make_maps(&da, B));
-        TRY(gemm_plan_init(&e->pl_qkv[l], e->wqkv[l], e->nqkv, d.hidden, e->xn, B, d.hidden, d.hidden, e->part,
+        TRY(gemm_plan_init(&e->pl_qkv[l], e->wqkv[l], e->nqkv, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_qkv,
                            e->nqkv, B, e->s_qkv, OUT_TRANSPOSED_F32, e->bn_dec));
-        TRY(gemm_plan_init(&e->pl_o[l], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->nq, e->nq, e->part, d.hidden,
+        TRY(gemm_plan_init(&e->pl_o[l], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->nq, e->nq, e->part_o, d.hidden,
                            B, e->s_o, OUT_TRANSPOSED_F32, e->bn_dec));
-        TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->part,
+        TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_gu,
                            2 * d.inter, B, e->s_gu, OUT_TRANSPOSED_F32, e->bn_dec));
-        TRY(gemm_plan_init(&e->pl_down[l], e->wdown[l], d.hidden, d.inter, e->act, B, d.inter, d.inter, e->part,
+        TRY(gemm_plan_init(&e->pl_down[l], e->wdown[l], d.hidden, d.inter, e->act, B, d.inter, d.inter, e->part_down,
                            d.hidden, B, e->s_down, OUT_TRANSPOSED_F32, e->bn_dec));
     }
     TRY(gemm_plan_init(&e->pl_head, e->lm_head, d.vocab, d.hidden, e->xn, B, d.hidden, d.hidden, e->logits, d.vocab,

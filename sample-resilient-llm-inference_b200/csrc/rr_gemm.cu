@@ -8,9 +8,17 @@
 // Two orientations of the same kernel:
 //   * prefill  (OUT_ROWMAJOR_BF16):  A = activations [T, K], B = weight [N, K]  -> C[T, N] bf16
 //   * decode   (OUT_TRANSPOSED_F32): A = weight [N, K] (UMMA M side, streamed once from HBM),
-//                                    B = activations [batch<=BN, K]; split-K over gridDim work
-//                                    items; fp32 partials P[z][b][n] reduced by the consumer
-//                                    kernel (rr_elementwise.cu).
+//                                    B = activations [batch<=BN, K]; fp32 partial planes
+//                                    P[z][b][n] reduced by the consumer kernel (rr_elementwise.cu).
+//     Work split for decode: either uniform split-K (splits planes), or stream-K (splits == 0):
+//     the tilesA x kblocks k-block units are dealt out to the CTAs as equal contiguous ranges that
+//     ignore tile boundaries, so all 148 SMs stream exactly the same number of weight bytes
+//     (no wave quantisation: 224 gate/up tiles on 148 SMs would otherwise run at 76 %).
+//     A tile cut by c CTA boundaries is written to planes 0..c; the schedule is static, so planes
+//     that are never written stay zero in a dedicated, once-zeroed partial buffer.
+//
+// PDL: the weight operand is constant, its first pipeline stages are requested before
+// griddepcontrol.wait; only the activation operand and the output wait for the preceding kernel.
 //
 // Replaces: the remote bedrock:InvokeModel call (reference iam/policy.json:8,
 // src/demo_cris.py:233-238) — there is no reference kernel; see DESIGN.md §kernels.
@@ -41,23 +49,63 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-struct TileCoord {
-    int a_tile, b_tile, z;
+struct WorkItem {
+    int a_tile, b_tile, z, kb0, kb1;
 };
 
-__device__ __forceinline__ TileCoord decode_work(int w, int tilesA, int tilesB, int splits) {
-    TileCoord t;
-    t.z = w % splits;
-    int q = w / splits;
-    int per_group = GROUP_A * tilesB;
-    int g = q / per_group;
-    int r = q - g * per_group;
-    int a0 = g * GROUP_A;
-    int ga = min(GROUP_A, tilesA - a0);
-    t.a_tile = a0 + r % ga;
-    t.b_tile = r / ga;
-    return t;
-}
+// Deterministic per-CTA sequence of work items; every warp role walks the same sequence.
+struct WorkSched {
+    int tilesA, tilesB, splits, kblocks, n_work, w;
+    long long cur, u_end, U;
+    int streamk;
+
+    __device__ __forceinline__ void init(int rowsA, int rowsB, int K, int splits_, int BN) {
+        tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
+        tilesB = (rowsB + BN - 1) / BN;
+        kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+        streamk = splits_ == 0;
+        splits = splits_;
+        if (streamk) {
+            U = (long long)tilesA * kblocks;
+            cur = (U * blockIdx.x) / gridDim.x;
+            u_end = (U * (blockIdx.x + 1)) / gridDim.x;
+        } else {
+            n_work = tilesA * tilesB * splits;
+            w = blockIdx.x;
+        }
+    }
+    __device__ __forceinline__ bool next(WorkItem& it) {
+        if (streamk) {
+            if (cur >= u_end) return false;
+            const int T = (int)(cur / kblocks);
+            const long long tile_u0 = (long long)T * kblocks;
+            it.a_tile = T;
+            it.b_tile = 0;
+            it.kb0 = (int)(cur - tile_u0);
+            const long long left = u_end - cur;
+            it.kb1 = (kblocks - it.kb0 < left) ? kblocks : it.kb0 + (int)left;
+            // plane = number of CTA range boundaries inside this tile before `cur`
+            const int c_first = (int)(((tile_u0 + 1) * gridDim.x + U - 1) / U) - 1;
+            it.z = (int)blockIdx.x - c_first;
+            cur += it.kb1 - it.kb0;
+            return true;
+        }
+        if (w >= n_work) return false;
+        it.z = w % splits;
+        const int q = w / splits;
+        const int per_group = GROUP_A * tilesB;
+        const int g = q / per_group;
+        const int r = q - g * per_group;
+        const int a0 = g * GROUP_A;
+        const int ga = min(GROUP_A, tilesA - a0);
+        it.a_tile = a0 + r % ga;
+        it.b_tile = r / ga;
+        it.kb0 = (int)(((long long)kblocks * it.z) / splits);
+        it.kb1 = (int)(((long long)kblocks * (it.z + 1)) / splits);
+        w += gridDim.x;
+        return true;
+    }
+};
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -81,11 +129,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     griddep_launch();   // PDL: the next kernel may start its prologue now
-
-    const int tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
-    const int tilesB = (rowsB + BN - 1) / BN;
-    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
-    const int n_work = tilesA * tilesB * splits;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
@@ -111,6 +154,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    WorkSched sched;
+    sched.init(rowsA, rowsB, K, splits, BN);
+    WorkItem t;
+
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
@@ -121,48 +168,39 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t polB = l2_policy_evict_last();
             int stage = 0;
             uint32_t phase = 0;
-            // PDL prefetch: the weight operand is constant, so the first kStages tiles of it are
-            // requested BEFORE waiting for the preceding kernel; only the activation operand waits.
-            // (decode: A = weights; prefill: B = weights.)
+            bool have = sched.next(t);
+            // PDL prefetch of the constant (weight) operand for the first `pre` k-blocks.
+            // (An additional L2 prefetch of the rest of the panel was measured SLOWER on B200:
+            //  5.12 -> 5.37 ms per decode step.)
             int pre = 0;
-            if (blockIdx.x < n_work) {
-                const TileCoord t = decode_work(blockIdx.x, tilesA, tilesB, splits);
-                const int kb0 = (int)(((long long)kblocks * t.z) / splits);
-                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
-                pre = min(kStages, kb1 - kb0);
+            if (have) {
+                pre = min(kStages, t.kb1 - t.kb0);
                 for (int i = 0; i < pre; ++i) {
                     mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
                     if (MODE == OUT_TRANSPOSED_F32)
-                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (kb0 + i) * BLOCK_K,
+                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.a_tile * BLOCK_A, polA);
                     else
-                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (kb0 + i) * BLOCK_K,
+                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.b_tile * BN, polB);
-                }
-                // (An L2 prefetch of the rest of the weight panel here was measured SLOWER on B200:
-                //  5.12 -> 5.37 ms per decode step; the 8 in-flight stages are the whole head start.)
-                griddep_wait();
-                for (int i = 0; i < pre; ++i) {
-                    if (MODE == OUT_TRANSPOSED_F32)
-                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (kb0 + i) * BLOCK_K,
-                                         t.b_tile * BN, polB);
-                    else
-                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (kb0 + i) * BLOCK_K,
-                                         t.a_tile * BLOCK_A, polA);
                 }
             }
-            bool first = true;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
-                int kb0 = (int)(((long long)kblocks * t.z) / splits);
-                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
-                if (first) {                       // the first `pre` k-blocks are already in flight
-                    first = false;
-                    kb0 += pre;
-                    stage = pre % kStages;
-                    phase = (pre == kStages) ? 1u : 0u;
+            griddep_wait();
+            if (have) {
+                for (int i = 0; i < pre; ++i) {
+                    if (MODE == OUT_TRANSPOSED_F32)
+                        tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (t.kb0 + i) * BLOCK_K,
+                                         t.b_tile * BN, polB);
+                    else
+                        tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (t.kb0 + i) * BLOCK_K,
+                                         t.a_tile * BLOCK_A, polA);
                 }
-                for (int kb = kb0; kb < kb1; ++kb) {
+                t.kb0 += pre;                          // already in flight
+                stage = pre % kStages;
+                phase = (pre == kStages) ? 1u : 0u;
+            }
+            while (have) {
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage],
@@ -174,6 +212,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         phase ^= 1;
                     }
                 }
+                have = sched.next(t);
             }
         }
     } else if (warp == 1) {
@@ -182,17 +221,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_A, BN);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                const TileCoord t = decode_work(w, tilesA, tilesB, splits);
-                const int kb0 = (int)(((long long)kblocks * t.z) / splits);
-                const int kb1 = (int)(((long long)kblocks * (t.z + 1)) / splits);
+            for (int it = 0; sched.next(t); ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint64_t adesc =
@@ -203,7 +238,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B inside the swizzle row: +2 in 16-byte units
                         umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                     (kb > kb0 || k > 0) ? 1u : 0u);
+                                     (kb > t.kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);   // smem slot free once these MMAs retire
                     if (++stage == kStages) {
@@ -218,10 +253,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
-        int it = 0;
         griddep_wait();                               // `out` may still be read by the preceding kernel
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-            const TileCoord t = decode_work(w, tilesA, tilesB, splits);
+        for (int it = 0; sched.next(t); ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -329,6 +362,24 @@ int num_sms() {
     return g_num_sms;
 }
 
+// stream-K geometry: number of CTAs and of partial planes for [rowsA, K] weights.
+int gemm_streamk_ctas(int rowsA, int K) {
+    const long long U = (long long)((rowsA + BLOCK_A - 1) / BLOCK_A) * ((K + BLOCK_K - 1) / BLOCK_K);
+    return (int)(U < num_sms() ? U : num_sms());
+}
+int gemm_streamk_planes(int rowsA, int K) {
+    const int tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A, kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const long long U = (long long)tilesA * kb;
+    const long long n = gemm_streamk_ctas(rowsA, K);
+    auto c_of = [&](long long x) { return (int)(((x + 1) * n + U - 1) / U) - 1; };
+    int planes = 1;
+    for (int T = 0; T < tilesA; ++T) {
+        const int p = c_of((long long)T * kb + kb - 1) - c_of((long long)T * kb) + 1;
+        if (p > planes) planes = p;
+    }
+    return planes;
+}
+
 template <int BN, int MODE>
 static int launch_one(const GemmPlan& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
@@ -340,21 +391,33 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
         if (e != cudaSuccess) return RR_ERR_CUDA;
         attr_set = true;
     }
-    const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
-    const int tilesB = (p.rowsB + BN - 1) / BN;
-    const int n_work = tilesA * tilesB * p.splits;
-    int grid = n_work < num_sms() ? n_work : num_sms();
-    if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
+    int grid;
+    if (p.streamk) {
+        grid = gemm_streamk_ctas(p.rowsA, p.K);
+    } else {
+        const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
+        const int tilesB = (p.rowsB + BN - 1) / BN;
+        const int n_work = tilesA * tilesB * p.splits;
+        grid = n_work < num_sms() ? n_work : num_sms();
+    }
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::kSmemBytes, st, p.tmA, p.tmB,
-                                p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows);
+                                p.out, p.rowsA, p.rowsB, p.K, p.streamk ? 0 : p.splits, p.ldo, p.ld_rows);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
+// splits >= 1: uniform split-K with `splits` planes.  splits == 0: stream-K (decode orientation, rowsB <= bn);
+// p->splits then holds the number of planes the consumer must sum (gemm_streamk_planes).
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn) {
     if (K % 8 != 0 || ldA % 8 != 0 || ldB % 8 != 0) return RR_ERR_ARG;
     if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256)) return RR_ERR_ARG;
     const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    p->streamk = 0;
+    if (splits == 0) {
+        if (mode != OUT_TRANSPOSED_F32 || rowsB > bn) return RR_ERR_ARG;
+        p->streamk = 1;
+        splits = gemm_streamk_planes(rowsA, K);
+    }
     if (splits < 1) splits = 1;
     if (splits > kblocks) splits = kblocks;
     if (mode == OUT_ROWMAJOR_BF16 && (splits != 1 || ldo % 8 != 0)) return RR_ERR_ARG;

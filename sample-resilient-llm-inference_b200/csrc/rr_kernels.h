@@ -18,10 +18,12 @@ enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1 };
 struct GemmPlan {
     CUtensorMap tmA, tmB;
     void* out;
-    int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas;
+    int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas, streamk;
 };
 
 int num_sms();
+int gemm_streamk_planes(int rowsA, int K);
+int gemm_streamk_ctas(int rowsA, int K);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows);
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn);

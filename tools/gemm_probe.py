@@ -14,7 +14,8 @@ def time_gemm(rowsA, rowsB, K, mode, bn, splits, iters=20, ncopies=4):
     if mode == 0:
         out = torch.empty(rowsA, rowsB, device="cuda", dtype=torch.bfloat16); ldo, ldr = rowsB, 0
     else:
-        out = torch.empty(splits, rowsB, rowsA, device="cuda", dtype=torch.float32); ldo, ldr = rowsA, rowsB
+        planes = splits if splits > 0 else lib.rr_gemm_streamk_planes(rowsA, K)
+        out = torch.zeros(planes, rowsB, rowsA, device="cuda", dtype=torch.float32); ldo, ldr = rowsA, rowsB
     def run(i):
         A = As[i % ncopies]
         rc = lib.rr_gemm_bf16(A.data_ptr(), rowsA, K, B.data_ptr(), rowsB, K, K, out.data_ptr(),
@@ -31,14 +32,15 @@ def time_gemm(rowsA, rowsB, K, mode, bn, splits, iters=20, ncopies=4):
 
 if __name__ == "__main__":
     print("decode orientation (weights streamed): rowsA=N_out rowsB=batch")
-    for name, N, K, splits_list in [("qkv", 6144, 4096, [1, 2, 3, 6]), ("o", 4096, 4096, [1, 4, 8]),
-                                    ("gate_up", 28672, 4096, [1, 2, 4]), ("down", 4096, 14336, [4, 7, 14]),
-                                    ("lm_head", 128256, 4096, [1])]:
+    for name, N, K, splits_list in [("qkv", 6144, 4096, [3, 0]), ("o", 4096, 4096, [4, 0]),
+                                    ("gate_up", 28672, 4096, [1, 0]), ("down", 4096, 14336, [4, 0]),
+                                    ("lm_head", 128256, 4096, [1, 0])]:
         for s in splits_list:
             for bn in (64,):
                 ms = time_gemm(N, 64, K, 1, bn, s, ncopies=max(2, int(300e6 / (N * K * 2)) + 1))
                 gb = N * K * 2 / ms / 1e6
                 print(f"  {name:8s} N={N:6d} K={K:5d} bn={bn} splits={s:2d}: {ms*1e3:8.1f} us  {gb:7.0f} GB/s")
+    if "--decode-only" in sys.argv: sys.exit(0)
     print("prefill orientation: rowsA=tokens rowsB=N_out")
     for name, T, N, K in [("qkv", 8192, 6144, 4096), ("gate_up", 8192, 28672, 4096), ("down", 8192, 4096, 14336),
                           ("qkv2k", 2048, 6144, 4096)]:
