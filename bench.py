@@ -368,7 +368,7 @@ def main():
                     "api": "Router.completion_batch -> rr_router_process + rr_engine_submit/rr_engine_wait (host buffers)"},
             "gpu_launches": int(sm[5].item() + 2 * K),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "decode step = 1 CUDA-graph launch (291 kernels; dominant: gemm_bf16_tcgen05<64,1> weight stream)",
+                         "traffic": None, "kernel": "decode step = 1 CUDA-graph launch (228 kernels with PDL edges; dominant: gemm_bf16_tcgen05<64,*> weight stream)",
                          "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms, "peak_source": peak_src},
             "prefill": {"tflops": pf_tflops, "peak_tflops_sustained": tf_peak, "frac": (pf_tflops / tf_peak) if pf_tflops else None,
                         "ms_per_burst": mx[4].item() / K},

@@ -45,6 +45,11 @@ const char* rr_last_cuda_error(void);
 /* Programmatic dependent launch between the library's kernels (default on; env RR_NO_PDL=1 turns it
  * off).  Returns the previous setting.  Must not change between capture and replay of an engine graph. */
 int rr_set_pdl(int enabled);
+/* Debug timeline: CTA 0 of every library kernel records (kernel id, start ns, ns when griddepcontrol.wait
+ * returned, end ns) with %globaltimer.  start allocates a device buffer; stop copies `*n` records
+ * (4 x uint64 each) to `out`. */
+int rr_debug_trace_start(int max_entries);
+int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n);
 
 /* ================================================================================================
  * 1. Router: admission + rpm/tpm bucket debit + backend pick + cooldown + fallback chain (K1).
@@ -139,7 +144,11 @@ int rr_tokenize(const uint8_t* text, size_t n_bytes, int32_t vocab, int32_t* ids
  *    Replaces the remote bedrock:InvokeModel prefill/decode (reference iam/policy.json:8,
  *    src/demo_cris.py:233-238).  All pointers are device pointers. */
 
-enum { RR_OUT_ROWMAJOR_BF16 = 0, RR_OUT_TRANSPOSED_F32 = 1 };
+enum { RR_OUT_ROWMAJOR_BF16 = 0, RR_OUT_TRANSPOSED_F32 = 1,
+       /* fused SiLU(gate)*up epilogues; the weight operand holds gate/up rows interleaved in 64-row blocks
+        * [g0..g63, u0..u63, g64..g127, u64..u127, ...] and the output is bf16 act[.., inter]: */
+       RR_OUT_TRANSPOSED_SILU = 2,   /* decode: A = interleaved weight [2*inter, K], out[b*ldo + n], splits = 1 */
+       RR_OUT_ROWMAJOR_SILU = 3 };   /* prefill: B = interleaved weight, bn = 256, out[a*ldo + n] */
 
 /* D[a,b] = sum_k A[a,k] B[b,k] on tcgen05 tensor cores (bf16 in, fp32 accumulate).
  * mode RR_OUT_ROWMAJOR_BF16:  out bf16 [rowsA, ldo], out[a*ldo + b]         (splits must be 1)
@@ -194,7 +203,12 @@ typedef struct rr_model_weights {
     const void* const* wdown;     /* n_layers x [hidden, inter] */
     const void* const* norm_attn; /* n_layers x [hidden] */
     const void* const* norm_mlp;  /* n_layers x [hidden] */
+    int32_t flags;                /* RR_WEIGHTS_* */
+    int32_t reserved;
 } rr_model_weights;
+/* wgu rows are interleaved in 64-row gate/up blocks [g0..g63, u0..u63, g64.., u64.., ...] instead of
+ * [gate; up]: enables the fused SiLU*mul GEMM epilogues (no separate activation kernel). */
+#define RR_WEIGHTS_WGU_INTERLEAVED64 1
 
 typedef struct rr_engine rr_engine;
 

@@ -71,7 +71,7 @@ class ModelWeights(C.Structure):
     _fields_ = [("embed", vp), ("lm_head", vp), ("final_norm", vp),
                 ("wqkv", C.POINTER(vp)), ("wo", C.POINTER(vp)), ("wgu", C.POINTER(vp)),
                 ("wdown", C.POINTER(vp)), ("norm_attn", C.POINTER(vp)),
-                ("norm_mlp", C.POINTER(vp))]
+                ("norm_mlp", C.POINTER(vp)), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class EngineOpts(C.Structure):
@@ -102,6 +102,8 @@ PROTOTYPES = {
     "rr_strerror": (C.c_char_p, [C.c_int]),
     "rr_last_cuda_error": (C.c_char_p, []),
     "rr_set_pdl": (C.c_int, [C.c_int]),
+    "rr_debug_trace_start": (C.c_int, [C.c_int]),
+    "rr_debug_trace_stop": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, c_i32p]),
     "rr_router_create": (C.c_int, [C.POINTER(DeploymentDesc), C.c_int, C.c_int, c_i32p, c_i32p,
                                    C.POINTER(RouterSettings), C.c_uint64, C.c_int,
                                    C.POINTER(vp)]),

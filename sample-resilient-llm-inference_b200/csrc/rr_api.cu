@@ -43,6 +43,46 @@ RR_API const char* rr_strerror(int rc) {
 
 RR_API const char* rr_last_cuda_error(void) { return g_last_cuda_error; }
 
+namespace rr {
+void rr_trace_set_gemm(unsigned long long*);
+void rr_trace_set_attn_decode(unsigned long long*);
+void rr_trace_set_attn(unsigned long long*);
+void rr_trace_set_elementwise(unsigned long long*);
+}
+static unsigned long long* g_trace_dev = nullptr;
+static int g_trace_cap = 0;
+
+// Debug timeline: (kernel id, start ns, dependency-resolved ns, end ns) of CTA 0 of every library kernel (globaltimer).
+RR_API int rr_debug_trace_start(int max_entries) {
+    if (max_entries < 1) return RR_INVALID_ARGUMENT;
+    if (g_trace_dev) cudaFree(g_trace_dev);
+    const size_t n = 2 + 4 * (size_t)max_entries;
+    if (cudaMalloc(&g_trace_dev, n * 8) != cudaSuccess) return RR_CUDA_ERROR;
+    cudaMemset(g_trace_dev, 0, n * 8);
+    unsigned long long cap = (unsigned long long)max_entries;
+    cudaMemcpy(g_trace_dev + 1, &cap, 8, cudaMemcpyHostToDevice);
+    g_trace_cap = max_entries;
+    rr_trace_set_gemm(g_trace_dev); rr_trace_set_attn_decode(g_trace_dev); rr_trace_set_attn(g_trace_dev);
+    rr_trace_set_elementwise(g_trace_dev);
+    return check_last();
+}
+// Stops tracing and copies up to max_entries (id, start, dep, end) records; returns the number recorded via *n.
+RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n) {
+    if (!g_trace_dev || !out || !n) return RR_INVALID_ARGUMENT;
+    cudaDeviceSynchronize();
+    rr_trace_set_gemm(nullptr); rr_trace_set_attn_decode(nullptr); rr_trace_set_attn(nullptr);
+    rr_trace_set_elementwise(nullptr);
+    unsigned long long cnt = 0;
+    cudaMemcpy(&cnt, g_trace_dev, 8, cudaMemcpyDeviceToHost);
+    int m = (int)(cnt < (unsigned long long)g_trace_cap ? cnt : g_trace_cap);
+    if (m > max_entries) m = max_entries;
+    cudaMemcpy(out, g_trace_dev + 2, (size_t)m * 32, cudaMemcpyDeviceToHost);
+    *n = m;
+    cudaFree(g_trace_dev);
+    g_trace_dev = nullptr;
+    return check_last();
+}
+
 RR_API int rr_set_pdl(int enabled) {
     int old = g_use_pdl;
     g_use_pdl = enabled ? 1 : 0;
@@ -150,6 +190,7 @@ RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_c
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.slot = slot; a.pos = pos;
     a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
     a.kv_splits = kv_splits < 1 ? 1 : kv_splits; a.ws = nullptr;
+    a.fuse_rope = 0; a.qkv.ptr = nullptr; a.rope_table = nullptr;
     { int rcm = decode_attn_make_maps(&a, n_slots); if (rcm != RR_OK) return rcm; }
     float* ws = nullptr;
     if (a.kv_splits > 1) {

@@ -49,7 +49,9 @@ prefill_attn_kernel(PrefillAttnArgs a) {
     uint8_t* sK = pf_smem + 16384;               // 2 x 64 x 256 B
     uint8_t* sV = pf_smem + 16384 + 32768;       // 2 x 64 x 256 B
     griddep_launch();
+    const int tr_slot = trace_begin(TR_ATTN_PF);
     griddep_wait();
+    trace_dep(tr_slot);
 
     const int seq = blockIdx.z, head = blockIdx.y;
     // heaviest (last) q tiles first
@@ -199,6 +201,7 @@ prefill_attn_kernel(PrefillAttnArgs a) {
             *reinterpret_cast<uint32_t*>(a.out + (size_t)(tok0 + qi1) * a.n_heads * HD + head * HD + d) =
                 pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
     }
+    trace_end(tr_slot);
 }
 
 void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
@@ -212,5 +215,7 @@ void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
     dim3 grid((a.max_len + PF_Q - 1) / PF_Q, a.n_heads, a.n_seqs);
     launch_pdl(prefill_attn_kernel, grid, dim3(PF_THREADS), (size_t)smem, st, a);
 }
+
+void rr_trace_set_attn(unsigned long long* p) { rr_trace_set_local(p); }
 
 }  // namespace rr

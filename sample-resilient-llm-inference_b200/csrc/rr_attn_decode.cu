@@ -27,7 +27,7 @@ constexpr int DT = 64;                  // tokens per unit
 constexpr int UNIT_BYTES = DT * HD * 2; // 16 KB
 constexpr int RING = 3;
 constexpr int DEC_THREADS = 160;        // 4 consumer warps + 1 producer warp
-constexpr int DEC_SMEM = RING * UNIT_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int DEC_SMEM = RING * UNIT_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 512 /*new k, v row*/ + 2048 /*q*/;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -61,18 +61,24 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + RING * UNIT_BYTES);
     uint64_t* empty_bar = full_bar + RING;
+    uint64_t* newkv_bar = empty_bar + RING;
+    __nv_bfloat16* newkv = reinterpret_cast<__nv_bfloat16*>(ring + RING * UNIT_BYTES + 128);   // [k 128 | v 128]
+    __nv_bfloat16* q_s = newkv + 2 * HD;                                                          // [8 heads][128]
 
     griddep_launch();
+    const int tr_slot = trace_begin(TR_ATTN_DEC);
     const int kvh = blockIdx.x, row = blockIdx.y, split = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
+        mbar_init(newkv_bar, 1);
         fence_barrier_init();
         tma_prefetch_desc(&a.tmK);
         tma_prefetch_desc(&a.tmV);
     }
     __syncthreads();
     griddep_wait();                         // slot/pos/q/KV come from the preceding kernels
+    trace_dep(tr_slot);
     const int slot = a.slot[row];
     if (slot < 0) return;
     const int ctx = a.pos[row] + 1;
@@ -83,19 +89,88 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     const int n_units = 2 * max(0, tile1 - tile0);
     const int row_base = (slot * a.n_kv_heads + kvh) * a.ctx_max;      // row in the [slots*kvh*ctx, 128] view
 
+    const int pos = ctx - 1;
+    const bool owns_new = a.fuse_rope && tile1 == n_tiles_all && tile1 > tile0;   // this split holds token `pos`
+
     if (warp == 4) {
         // ===================== producer: TMA units K0 V0 K1 V1 ... =====================
-        if (elect_one()) {
-            for (int u = 0; u < n_units; ++u) {
-                const int s = u % RING;
-                if (u >= RING) mbar_wait(&empty_bar[s], ((u / RING) - 1) & 1);
-                const CUtensorMap* tm = (u & 1) ? &a.tmV : &a.tmK;
-                const int r0 = row_base + (tile0 + (u >> 1)) * DT;
-                mbar_arrive_expect_tx(&full_bar[s], UNIT_BYTES);
-                tma_load_2d(ring + s * UNIT_BYTES, tm, &full_bar[s], 0, r0);
-                tma_load_2d(ring + s * UNIT_BYTES + 8192, tm, &full_bar[s], 64, r0);
+        const bool leader = elect_one();
+        auto issue = [&](int u) {
+            const int s = u % RING;
+            const CUtensorMap* tm = (u & 1) ? &a.tmV : &a.tmK;
+            const int r0 = row_base + (tile0 + (u >> 1)) * DT;
+            mbar_arrive_expect_tx(&full_bar[s], UNIT_BYTES);
+            tma_load_2d(ring + s * UNIT_BYTES, tm, &full_bar[s], 0, r0);
+            tma_load_2d(ring + s * UNIT_BYTES + 8192, tm, &full_bar[s], 64, r0);
+        };
+        const int first = min(RING, n_units);
+        if (leader)
+            for (int u = 0; u < first; ++u) issue(u);
+        if (a.fuse_rope) {
+            // K6 fused.  Rotated queries of the G heads -> smem (lane owns rotation pairs i = 2*lane, 2*lane+1 of
+            // every head); if this CTA holds token `pos`: rotate the new key, append k / v (bf16) to the cache and
+            // publish the row in smem.  All loads of one split plane are issued together (one latency per plane);
+            // the whole block overlaps the flight of the first K/V tiles.
+            const int i = 2 * lane;
+            const int kcol = a.n_heads * HD + kvh * HD, vcol = (a.n_heads + a.n_kv_heads) * HD + kvh * HD;
+            const float4 cs = *reinterpret_cast<const float4*>(a.rope_table + (size_t)pos * 64 + i);
+            float2 lo[G], hi[G];
+            float2 klo = make_float2(0.f, 0.f), khi = klo, v0 = klo, v1 = klo;
+#pragma unroll
+            for (int h = 0; h < G; ++h) lo[h] = hi[h] = make_float2(0.f, 0.f);
+            for (int z = 0; z < a.qkv.n_splits; ++z) {
+                const float* pl = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)z * a.qkv.split_stride +
+                                  (size_t)row * a.qkv.ld;
+                float2 tl[G], th[G];
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    tl[h] = *reinterpret_cast<const float2*>(pl + (kvh * G + h) * HD + i);
+                    th[h] = *reinterpret_cast<const float2*>(pl + (kvh * G + h) * HD + 64 + i);
+                }
+                float2 t0 = klo, t1 = klo, t2 = klo, t3 = klo;
+                if (owns_new) {
+                    t0 = *reinterpret_cast<const float2*>(pl + kcol + i);
+                    t1 = *reinterpret_cast<const float2*>(pl + kcol + 64 + i);
+                    t2 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane);
+                    t3 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane + 2);
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) { lo[h].x += tl[h].x; lo[h].y += tl[h].y; hi[h].x += th[h].x; hi[h].y += th[h].y; }
+                if (owns_new) {
+                    klo.x += t0.x; klo.y += t0.y; khi.x += t1.x; khi.y += t1.y;
+                    v0.x += t2.x; v0.y += t2.y; v1.x += t3.x; v1.y += t3.y;
+                }
             }
+#pragma unroll
+            for (int h = 0; h < G; ++h) {
+                *reinterpret_cast<uint32_t*>(q_s + h * HD + i) =
+                    pack_bf16(lo[h].x * cs.x - hi[h].x * cs.y, lo[h].y * cs.z - hi[h].y * cs.w);
+                *reinterpret_cast<uint32_t*>(q_s + h * HD + 64 + i) =
+                    pack_bf16(hi[h].x * cs.x + lo[h].x * cs.y, hi[h].y * cs.z + lo[h].y * cs.w);
+            }
+            if (owns_new) {
+                const uint32_t k_lo = pack_bf16(klo.x * cs.x - khi.x * cs.y, klo.y * cs.z - khi.y * cs.w);
+                const uint32_t k_hi = pack_bf16(khi.x * cs.x + klo.x * cs.y, khi.y * cs.z + klo.y * cs.w);
+                uint2 vv;
+                vv.x = pack_bf16(v0.x, v0.y);
+                vv.y = pack_bf16(v1.x, v1.y);
+                __nv_bfloat16* kdst = const_cast<__nv_bfloat16*>(a.k_cache) + ((size_t)row_base + pos) * HD;
+                __nv_bfloat16* vdst = const_cast<__nv_bfloat16*>(a.v_cache) + ((size_t)row_base + pos) * HD;
+                *reinterpret_cast<uint32_t*>(kdst + i) = k_lo;
+                *reinterpret_cast<uint32_t*>(kdst + 64 + i) = k_hi;
+                *reinterpret_cast<uint2*>(vdst + 4 * lane) = vv;
+                *reinterpret_cast<uint32_t*>(newkv + i) = k_lo;
+                *reinterpret_cast<uint32_t*>(newkv + 64 + i) = k_hi;
+                *reinterpret_cast<uint2*>(newkv + HD + 4 * lane) = vv;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(newkv_bar);      // q (and the new k / v row) are in smem
         }
+        if (leader)
+            for (int u = first; u < n_units; ++u) {
+                mbar_wait(&empty_bar[u % RING], ((u / RING) - 1) & 1);
+                issue(u);
+            }
         return;
     }
 
@@ -103,7 +178,14 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     const int g = lane >> 2, t = lane & 3;
     // Q^T B-fragments: b0 = Q[head g][16ks + 2t, +1], b1 = Q[head g][16ks + 8 + 2t, +1]; heads >= G are zero
     uint32_t qb[8][2];
-    {
+    if (a.fuse_rope) {
+        mbar_wait(newkv_bar, 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            qb[ks][0] = g < G ? *reinterpret_cast<const uint32_t*>(q_s + g * HD + ks * 16 + 2 * t) : 0u;
+            qb[ks][1] = g < G ? *reinterpret_cast<const uint32_t*>(q_s + g * HD + ks * 16 + 8 + 2 * t) : 0u;
+        }
+    } else {
         const __nv_bfloat16* qrow = a.q + (size_t)row * a.n_heads * HD + (size_t)(kvh * G + g) * HD;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -111,6 +193,8 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             qb[ks][1] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + 2 * t) : 0u;
         }
     }
+    const int patch_tile = owns_new ? pos / DT : -1;                  // tile whose staged copy lacks token `pos`
+    const bool patch_warp = ((pos % DT) >> 4) == warp;
     const float sc = a.scale * 1.4426950408889634f;
     float o[8][4];
 #pragma unroll
@@ -125,6 +209,12 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             const int s = u % RING;
             mbar_wait(&full_bar[s], (u / RING) & 1);
             const uint32_t base = ring_u + s * UNIT_BYTES;
+            if (tile == patch_tile && patch_warp) {          // the cache row of `pos` was written after/while TMA read it
+                if (lane < 16)
+                    *reinterpret_cast<uint4*>(ring + s * UNIT_BYTES + unit_off(pos % DT, lane)) =
+                        *reinterpret_cast<const uint4*>(newkv + lane * 8);
+                __syncwarp();
+            }
             float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -167,6 +257,12 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             const int s2 = (u + 1) % RING;
             mbar_wait(&full_bar[s2], ((u + 1) / RING) & 1);
             const uint32_t vbase = ring_u + s2 * UNIT_BYTES;
+            if (tile == patch_tile && patch_warp) {
+                if (lane < 16)
+                    *reinterpret_cast<uint4*>(ring + s2 * UNIT_BYTES + unit_off(pos % DT, lane)) =
+                        *reinterpret_cast<const uint4*>(newkv + HD + lane * 8);
+                __syncwarp();
+            }
 #pragma unroll
             for (int mt = 0; mt < 8; ++mt) {
                 uint32_t va[4];
@@ -221,6 +317,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             if (dp == 0) { w[HD] = M; w[HD + 1] = L; }
         }
     }
+    trace_end(tr_slot);
 }
 
 // combine split-KV partials: grid (n_heads, rows), 64 threads (dim pairs)
@@ -285,5 +382,7 @@ void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st) {
         default: break;
     }
 }
+
+void rr_trace_set_attn_decode(unsigned long long* p) { rr_trace_set_local(p); }
 
 }  // namespace rr

@@ -23,6 +23,7 @@ __device__ __forceinline__ float4 part_load4(const PartIn& p, int row, int col) 
     }
     const float* base = reinterpret_cast<const float*>(p.ptr) + (size_t)row * p.ld + col;
     float4 acc = *reinterpret_cast<const float4*>(base);
+#pragma unroll 8
     for (int z = 1; z < p.n_splits; ++z) {
         const float4 t = *reinterpret_cast<const float4*>(base + (size_t)z * p.split_stride);
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
@@ -45,7 +46,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __global__ void embed_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                              float* __restrict__ x, int hidden, const int32_t* __restrict__ row_active) {
     griddep_launch();
+    const int tr_slot = trace_begin(TR_EMBED);
     griddep_wait();
+    trace_dep(tr_slot);
     const int row = blockIdx.x;
     if (row_active && row_active[row] < 0) return;
     const int id = ids[row];
@@ -58,6 +61,7 @@ __global__ void embed_kernel(const int32_t* __restrict__ ids, const __nv_bfloat1
         *reinterpret_cast<float4*>(dst + c) = a;
         *reinterpret_cast<float4*>(dst + c + 4) = b;
     }
+    trace_end(tr_slot);
 }
 
 void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int rows, int hidden,
@@ -69,29 +73,32 @@ void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int 
 // ---- K4 residual add + RMSNorm (+ split-K reduce) ------------------------------------------------
 // One CTA per row; the row (hidden <= 8192) stays in registers between the sum-of-squares pass and
 // the normalise pass: x and the split planes are read exactly once.
-constexpr int NORM_THREADS = 256;
-constexpr int NORM_MAXV = 8;      // float4 per thread -> hidden <= 8192
+// Decode (few rows, latency-bound): 1024 threads, one float4 each, so every load of a thread is independent.
+// Prefill (thousands of rows, bandwidth-bound): 256 threads, 4 float4 each.
 
-__global__ void __launch_bounds__(NORM_THREADS)
+template <int THREADS, int MAXV>
+__global__ void __launch_bounds__(THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
                    __nv_bfloat16* __restrict__ xn, int hidden, float eps) {
     __shared__ float red[32];
     griddep_launch();
+    const int tr_slot = trace_begin(TR_NORM);
     const int row = blockIdx.x;
     float* xr = x + (size_t)row * hidden;
     // norm weights are constants: fetch them before waiting for the producer
-    uint2 wv[NORM_MAXV];
+    uint2 wv[MAXV];
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
-        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
         if (c < hidden) wv[i] = *reinterpret_cast<const uint2*>(w + c);
     }
     griddep_wait();
-    float4 v[NORM_MAXV];
+    trace_dep(tr_slot);
+    float4 v[MAXV];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
-        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
         if (c < hidden) {
             v[i] = *reinterpret_cast<float4*>(xr + c);
             if (part.ptr) {
@@ -106,8 +113,8 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
     const float inv = rsqrtf(ss / (float)hidden + eps);
     __nv_bfloat16* out = xn + (size_t)row * hidden;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
-        const int c = (threadIdx.x + i * NORM_THREADS) * 4;
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
         if (c < hidden) {
             uint2 o;
             o.x = pack_bf16(v[i].x * inv * bf16_lo(wv[i].x), v[i].y * inv * bf16_hi(wv[i].x));
@@ -115,19 +122,25 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
             *reinterpret_cast<uint2*>(out + c) = o;
         }
     }
+    trace_end(tr_slot);
 }
 
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
                         int hidden, float eps, cudaStream_t st) {
-    if (rows <= 0 || hidden > NORM_THREADS * 4 * NORM_MAXV) return;
-    launch_pdl(add_rmsnorm_kernel, dim3(rows), dim3(NORM_THREADS), 0, st, x, part, w, xn, hidden, eps);
+    if (rows <= 0 || hidden > 8192) return;
+    if (rows <= 256)
+        launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps);
+    else
+        launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps);
 }
 
 // ---- SiLU(gate) * up -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(PartIn gu, __nv_bfloat16* __restrict__ act, int inter) {
     griddep_launch();
+    const int tr_slot = trace_begin(TR_SILU);
     griddep_wait();
+    trace_dep(tr_slot);
     const int row = blockIdx.y;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c >= inter) return;
@@ -138,6 +151,7 @@ silu_mul_kernel(PartIn gu, __nv_bfloat16* __restrict__ act, int inter) {
     o.x = pack_bf16(f(g.x, u.x), f(g.y, u.y));
     o.y = pack_bf16(f(g.z, u.z), f(g.w, u.w));
     *reinterpret_cast<uint2*>(act + (size_t)row * inter + c) = o;
+    trace_end(tr_slot);
 }
 
 void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st) {
@@ -183,7 +197,9 @@ __device__ __forceinline__ float2 part_load2(const PartIn& p, int row, int col) 
 __global__ void __launch_bounds__(256)
 rope_kv_kernel(RopeArgs a) {
     griddep_launch();
+    const int tr_slot = trace_begin(TR_ROPE);
     griddep_wait();
+    trace_dep(tr_slot);
     const int row = blockIdx.x;
     const int slot = a.slot[row];
     if (slot < 0) return;
@@ -227,6 +243,7 @@ rope_kv_kernel(RopeArgs a) {
             *reinterpret_cast<uint2*>(dst) = o;
         }
     }
+    trace_end(tr_slot);
 }
 
 void launch_rope_kv(const RopeArgs& a, cudaStream_t st) {
@@ -241,7 +258,9 @@ argmax_kernel(PartIn logits, int vocab, int32_t* __restrict__ out_tok, float* __
     __shared__ float s_v[32];
     __shared__ int s_i[32];
     griddep_launch();
+    const int tr_slot = trace_begin(TR_ARGMAX);
     griddep_wait();
+    trace_dep(tr_slot);
     const int row = blockIdx.x;
     if (row_active && row_active[row] < 0) return;
     const float* r = reinterpret_cast<const float*>(logits.ptr) + (size_t)row * logits.ld;
@@ -283,6 +302,7 @@ argmax_kernel(PartIn logits, int vocab, int32_t* __restrict__ out_tok, float* __
             if (pos_inc) pos_inc[row] += 1;
         }
     }
+    trace_end(tr_slot);
 }
 
 void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
@@ -290,5 +310,7 @@ void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* 
     if (rows <= 0) return;
     launch_pdl(argmax_kernel, dim3(rows), dim3(1024), 0, st, logits, vocab, out_tok, out_val, row_active, pos_inc);
 }
+
+void rr_trace_set_elementwise(unsigned long long* p) { rr_trace_set_local(p); }
 
 }  // namespace rr

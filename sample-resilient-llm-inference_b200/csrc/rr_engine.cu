@@ -103,6 +103,7 @@ struct rr_engine {
     std::vector<DecodeAttnArgs> attn_args;   // per layer (TMA maps of that layer's K / V cache)
     GemmPlan pl_head, pl_head_pf;
     int s_qkv, s_o, s_gu, s_down;
+    bool fuse_silu = false;           // wgu interleaved + one gate/up plane: SiLU*mul lives in the GEMM epilogue
     cudaGraphExec_t graph = nullptr;
     bool warmed = false;
 
@@ -189,18 +190,13 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
         __nv_bfloat16* kc = e->kcache + (size_t)l * e->kv_layer_stride;
         __nv_bfloat16* vc = e->vcache + (size_t)l * e->kv_layer_stride;
         if (gemm_launch(e->pl_qkv[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        RopeArgs ra;
-        ra.qkv = part_f32(e->part_qkv, e->s_qkv, B, e->nqkv);
-        ra.q_out = e->qbuf; ra.k_cache = kc; ra.v_cache = vc; ra.slot = e->d_slot; ra.pos = e->d_pos;
-        ra.rows = B; ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max;
-        ra.theta = d.rope_theta; ra.table = e->rope_table;
-        launch_rope_kv(ra, s); ++nl;
+        // RoPE + KV append are fused into the attention kernel (reads the QKV split-K planes directly)
         launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
         if (gemm_launch(e->pl_o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
                            e->xn, B, d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(e->pl_gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        launch_silu_mul(part_f32(e->part_gu, e->s_gu, B, 2 * d.inter), e->act, B, d.inter, s); ++nl;
+        if (!e->fuse_silu) { launch_silu_mul(part_f32(e->part_gu, e->s_gu, B, 2 * d.inter), e->act, B, d.inter, s); ++nl; }
         if (gemm_launch(e->pl_down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         const void* nw = (l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm;
         launch_add_rmsnorm(e->x, part_f32(e->part_down, e->s_down, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
@@ -258,8 +254,12 @@ static int get_pf_plans(rr_engine* e, int T, rr_engine::PfPlans** out) {
         rc = gemm_plan_init(&P.o[l], e->pattn, T, e->nq, e->wo[l], d.hidden, e->nq, e->nq, e->po, d.hidden, 0, 1,
                             OUT_ROWMAJOR_BF16, 256);
         if (rc) return rc;
-        rc = gemm_plan_init(&P.gu[l], e->pxn, T, d.hidden, e->wgu[l], 2 * d.inter, d.hidden, d.hidden, e->pgu,
-                            2 * d.inter, 0, 1, OUT_ROWMAJOR_BF16, 256);
+        if (e->fuse_silu)
+            rc = gemm_plan_init(&P.gu[l], e->pxn, T, d.hidden, e->wgu[l], 2 * d.inter, d.hidden, d.hidden, e->pact,
+                                d.inter, 0, 1, OUT_ROWMAJOR_SILU, 256);
+        else
+            rc = gemm_plan_init(&P.gu[l], e->pxn, T, d.hidden, e->wgu[l], 2 * d.inter, d.hidden, d.hidden, e->pgu,
+                                2 * d.inter, 0, 1, OUT_ROWMAJOR_BF16, 256);
         if (rc) return rc;
         rc = gemm_plan_init(&P.down[l], e->pact, T, d.inter, e->wdown[l], d.hidden, d.inter, d.inter, e->po,
                             d.hidden, 0, 1, OUT_ROWMAJOR_BF16, 256);
@@ -325,7 +325,7 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
                            d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(P->gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        launch_silu_mul(part_bf16(e->pgu, 2 * d.inter), e->pact, T, d.inter, s); ++nl;
+        if (!e->fuse_silu) { launch_silu_mul(part_bf16(e->pgu, 2 * d.inter), e->pact, T, d.inter, s); ++nl; }
         if (gemm_launch(P->down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         const void* nw = (l + 1 < d.n_layers) ? e->norm_attn[l + 1] : e->final_norm;
         launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)nw, e->pxn, T, d.hidden,
@@ -503,6 +503,9 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     // gate/up by 5 % and costs extra planes for the consumers: 4.55 -> 4.92 ms per decode step.)
     e->s_qkv = pick_splits(e->nqkv, d.hidden); e->s_o = pick_splits(d.hidden, e->nq);
     e->s_gu = pick_splits(2 * d.inter, d.hidden); e->s_down = pick_splits(d.hidden, d.inter);
+    e->fuse_silu = (w->flags & RR_WEIGHTS_WGU_INTERLEAVED64) && e->s_gu == 1 && e->bn_dec >= 32 &&
+                   (2 * d.inter) % 128 == 0;
+    if ((w->flags & RR_WEIGHTS_WGU_INTERLEAVED64) && !e->fuse_silu) { rr_engine_destroy(e); return RR_INVALID_ARGUMENT; }
     TRY(dalloc(e, &e->d_tok, B)); TRY(dalloc(e, &e->d_pos, B)); TRY(dalloc(e, &e->d_slot, B));
     TRYC(cudaMemset(e->d_slot, 0xff, sizeof(int32_t) * B));
     TRY(dalloc(e, &e->x, (size_t)B * d.hidden));
@@ -553,13 +556,18 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         da.pos = e->d_pos; da.rows = B; da.n_heads = d.n_heads; da.n_kv_heads = d.n_kv_heads;
         da.ctx_max = opts->ctx_max; da.scale = 1.0f / sqrtf((float)d.head_dim); da.ws = e->attn_ws;
         da.kv_splits = e->kv_splits;
+        da.fuse_rope = 1; da.qkv = part_f32(e->part_qkv, e->s_qkv, B, e->nqkv); da.rope_table = e->rope_table;
         TRY(decode_attn_make_maps(&da, B));
         TRY(gemm_plan_init(&e->pl_qkv[l], e->wqkv[l], e->nqkv, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_qkv,
                            e->nqkv, B, e->s_qkv, OUT_TRANSPOSED_F32, e->bn_dec));
         TRY(gemm_plan_init(&e->pl_o[l], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->nq, e->nq, e->part_o, d.hidden,
                            B, e->s_o, OUT_TRANSPOSED_F32, e->bn_dec));
-        TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_gu,
-                           2 * d.inter, B, e->s_gu, OUT_TRANSPOSED_F32, e->bn_dec));
+        if (e->fuse_silu)
+            TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->act,
+                               d.inter, B, 1, OUT_TRANSPOSED_SILU, e->bn_dec));
+        else
+            TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_gu,
+                               2 * d.inter, B, e->s_gu, OUT_TRANSPOSED_F32, e->bn_dec));
         TRY(gemm_plan_init(&e->pl_down[l], e->wdown[l], d.hidden, d.inter, e->act, B, d.inter, d.inter, e->part_down,
                            d.hidden, B, e->s_down, OUT_TRANSPOSED_F32, e->bn_dec));
     }

@@ -47,7 +47,15 @@ struct GemmCfg {
     static constexpr uint32_t kTmemCols =
         (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSiluStageBytes = 2 * 32 * 64 * 4;   // OUT_TRANSPOSED_SILU: up-row exchange, 2 x [32 cols][64 rows] fp32
 };
+template <int MODE>
+__host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }
+template <int BN, int MODE>
+constexpr int gemm_smem_bytes() {
+    return GemmCfg<BN>::kSmemBytes + (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN>::kSiluStageBytes : 0);
+}
+__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.f + __expf(-g)) * u; }
 
 struct WorkItem {
     int a_tile, b_tile, z, kb0, kb1;
@@ -129,6 +137,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     griddep_launch();   // PDL: the next kernel may start its prologue now
+    const int tr_slot = trace_begin(decode_orient<MODE>() ? TR_GEMM_DEC : TR_GEMM_PF);
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
@@ -163,7 +172,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
             // Streamed-once operand (decode weights) should not displace the KV cache in L2;
             // the small re-read operand is kept.
-            const uint64_t polA = (MODE == OUT_TRANSPOSED_F32) ? l2_policy_evict_first()
+            const uint64_t polA = decode_orient<MODE>() ? l2_policy_evict_first()
                                                                : l2_policy_evict_last();
             const uint64_t polB = l2_policy_evict_last();
             int stage = 0;
@@ -177,7 +186,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 pre = min(kStages, t.kb1 - t.kb0);
                 for (int i = 0; i < pre; ++i) {
                     mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
-                    if (MODE == OUT_TRANSPOSED_F32)
+                    if (decode_orient<MODE>())
                         tma_load_2d_hint(smemA + i * Cfg::kStageBytesA, &tmA, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.a_tile * BLOCK_A, polA);
                     else
@@ -186,9 +195,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             griddep_wait();
+            trace_dep(tr_slot);
             if (have) {
                 for (int i = 0; i < pre; ++i) {
-                    if (MODE == OUT_TRANSPOSED_F32)
+                    if (decode_orient<MODE>())
                         tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.b_tile * BN, polB);
                     else
@@ -262,6 +272,75 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             constexpr int CH = (BN >= 32) ? 32 : 16;
+            if constexpr (MODE == OUT_TRANSPOSED_SILU) {
+                // gate/up rows are interleaved in blocks of 64: lanes 0..63 of the tile hold gate rows, lanes 64..127 the
+                // matching up rows.  The up warps hand their values over through smem ([col][row] -> conflict-free), the
+                // gate warps write act[b][n] = silu(g) * u as bf16.  rowsA = 2 * inter (interleaved), ldo = inter.
+                float* stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+                const bool is_up = quarter >= 2;
+                const int r64 = (quarter & 1) * 32 + lane;
+                const int n = t.a_tile * 64 + r64;
+                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    float* buf = stage + ((c >> 5) & 1) * (32 * 64);
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr0 + c, v);
+                    tmem_ld_wait();
+                    if (is_up) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (!is_up && 2 * n < rowsA) {
+                        const int b0 = t.b_tile * BN + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int b = b0 + j;
+                            if (b < rowsB)
+                                act[(size_t)b * ldo + n] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
+                        }
+                    }
+                }
+            } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
+                // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
+                // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
+                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
+                const int n_out = rowsB >> 1;
+#pragma unroll 1
+                for (int hb = 0; hb < BN / 128; ++hb) {
+#pragma unroll 1
+                    for (int c = 0; c < 64; c += 32) {
+                        uint32_t vg[32], vu[32];
+                        tmem_ld_32x32b_x32(taddr0 + hb * 128 + c, vg);
+                        tmem_ld_32x32b_x32(taddr0 + hb * 128 + 64 + c, vu);
+                        tmem_ld_wait();
+                        const int col = t.b_tile * (BN / 2) + hb * 64 + c;
+                        if (a_row < rowsA) {
+                            __nv_bfloat16* dst = act + (size_t)a_row * ldo + col;
+                            if (col + 32 <= n_out) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    uint4 pk;
+                                    pk.x = pack_bf16(silu_mul(__uint_as_float(vg[j + 0]), __uint_as_float(vu[j + 0])),
+                                                     silu_mul(__uint_as_float(vg[j + 1]), __uint_as_float(vu[j + 1])));
+                                    pk.y = pack_bf16(silu_mul(__uint_as_float(vg[j + 2]), __uint_as_float(vu[j + 2])),
+                                                     silu_mul(__uint_as_float(vg[j + 3]), __uint_as_float(vu[j + 3])));
+                                    pk.z = pack_bf16(silu_mul(__uint_as_float(vg[j + 4]), __uint_as_float(vu[j + 4])),
+                                                     silu_mul(__uint_as_float(vg[j + 5]), __uint_as_float(vu[j + 5])));
+                                    pk.w = pack_bf16(silu_mul(__uint_as_float(vg[j + 6]), __uint_as_float(vu[j + 6])),
+                                                     silu_mul(__uint_as_float(vg[j + 7]), __uint_as_float(vu[j + 7])));
+                                    *reinterpret_cast<uint4*>(dst + j) = pk;
+                                }
+                            } else {
+                                for (int j = 0; j < 32; ++j)
+                                    if (col + j < n_out)
+                                        dst[j] = __float2bfloat16(silu_mul(__uint_as_float(vg[j]), __uint_as_float(vu[j])));
+                            }
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN; c += CH) {
                 uint32_t v[32];
@@ -306,6 +385,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
             }
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -314,6 +394,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     tcgen05_fence_before();
     __syncthreads();
+    trace_end(tr_slot);
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -387,7 +468,7 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN, MODE>());
         if (e != cudaSuccess) return RR_ERR_CUDA;
         attr_set = true;
     }
@@ -400,7 +481,7 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
         const int n_work = tilesA * tilesB * p.splits;
         grid = n_work < num_sms() ? n_work : num_sms();
     }
-    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::kSmemBytes, st, p.tmA, p.tmB,
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, MODE>(), st, p.tmA, p.tmB,
                                 p.out, p.rowsA, p.rowsB, p.K, p.streamk ? 0 : p.splits, p.ldo, p.ld_rows);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
@@ -421,6 +502,10 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     if (splits < 1) splits = 1;
     if (splits > kblocks) splits = kblocks;
     if (mode == OUT_ROWMAJOR_BF16 && (splits != 1 || ldo % 8 != 0)) return RR_ERR_ARG;
+    // fused SiLU*mul epilogues: weights row-interleaved in 64-row gate/up blocks, one plane, bf16 act output
+    if (mode == OUT_TRANSPOSED_SILU && (splits != 1 || p->streamk || bn < 32 || rowsA % 128 != 0)) return RR_ERR_ARG;
+    if (mode == OUT_ROWMAJOR_SILU && (splits != 1 || bn != 256 || rowsB % 128 != 0 || ldo % 8 != 0)) return RR_ERR_ARG;
+    if (mode < 0 || mode > OUT_ROWMAJOR_SILU) return RR_ERR_ARG;
     p->rowsA = rowsA; p->rowsB = rowsB; p->K = K; p->out = out; p->ldo = ldo; p->ld_rows = ld_rows;
     p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
     int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
@@ -429,10 +514,17 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
 }
 
 int gemm_launch(const GemmPlan& p, cudaStream_t st) {
-#define RR_CASE(BN_)                                                                   \
-    case BN_:                                                                          \
-        return p.mode == OUT_ROWMAJOR_BF16 ? launch_one<BN_, OUT_ROWMAJOR_BF16>(p, st) \
-                                           : launch_one<BN_, OUT_TRANSPOSED_F32>(p, st);
+#define RR_CASE(BN_)                                                                                  \
+    case BN_:                                                                                         \
+        if (p.mode == OUT_ROWMAJOR_BF16) return launch_one<BN_, OUT_ROWMAJOR_BF16>(p, st);             \
+        if (p.mode == OUT_TRANSPOSED_F32) return launch_one<BN_, OUT_TRANSPOSED_F32>(p, st);           \
+        if constexpr (BN_ >= 32) {                                                                    \
+            if (p.mode == OUT_TRANSPOSED_SILU) return launch_one<BN_, OUT_TRANSPOSED_SILU>(p, st);     \
+        }                                                                                             \
+        if constexpr (BN_ == 256) {                                                                   \
+            if (p.mode == OUT_ROWMAJOR_SILU) return launch_one<BN_, OUT_ROWMAJOR_SILU>(p, st);         \
+        }                                                                                             \
+        return RR_ERR_ARG;
     switch (p.bn) {
         RR_CASE(16)
         RR_CASE(32)
@@ -443,5 +535,7 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
 #undef RR_CASE
     return RR_ERR_ARG;
 }
+
+void rr_trace_set_gemm(unsigned long long* p) { rr_trace_set_local(p); }
 
 }  // namespace rr

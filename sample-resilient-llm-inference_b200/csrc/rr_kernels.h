@@ -13,7 +13,7 @@ namespace rr {
 #define RR_ERR_ARG RR_INVALID_ARGUMENT
 #define RR_ERR_CUDA RR_CUDA_ERROR
 
-enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1 };
+enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1, OUT_TRANSPOSED_SILU = 2, OUT_ROWMAJOR_SILU = 3 };
 
 struct GemmPlan {
     CUtensorMap tmA, tmB;
@@ -79,6 +79,12 @@ struct DecodeAttnArgs {
     float* ws;                // split-KV workspace (may be null when kv_splits == 1)
     int kv_splits;
     CUtensorMap tmK, tmV;     // [n_slots*n_kv_heads*ctx_max, 128] views of the caches, box {64, 64}, SW128
+    // fused RoPE + KV append (decode): q/k/v of the current token come straight from the QKV GEMM's
+    // split-K planes; q is rotated into the MMA fragments, k/v are rotated, appended to the cache and
+    // patched into the staged tile.  fuse_rope == 0: `q` holds rotated bf16 queries (rope_kv_kernel ran).
+    int fuse_rope;
+    PartIn qkv;
+    const float2* rope_table;
 };
 int decode_attn_make_maps(DecodeAttnArgs* a, int n_slots);   // fills tmK / tmV (ctx_max % 64 == 0)
 void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st);

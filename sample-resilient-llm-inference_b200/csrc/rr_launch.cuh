@@ -13,6 +13,35 @@ namespace rr {
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- optional in-kernel timeline (debug): CTA (0,0,0) thread 0 of every kernel records
+// (kernel id, globaltimer at start, after griddepcontrol.wait, at end) into a device buffer; rr_debug_trace_*.
+// Each translation unit owns its copy of the pointer (no -rdc); rr_api.cu sets them all.
+static __device__ unsigned long long* rr_trace_ptr = nullptr;
+static inline void rr_trace_set_local(unsigned long long* p) { cudaMemcpyToSymbol(rr_trace_ptr, &p, sizeof(p)); }
+enum TraceId { TR_GEMM_DEC = 1, TR_GEMM_PF = 2, TR_ATTN_DEC = 3, TR_ATTN_PF = 4, TR_NORM = 5, TR_ROPE = 6,
+               TR_SILU = 7, TR_EMBED = 8, TR_ARGMAX = 9, TR_COMBINE = 10, TR_MISC = 11 };
+__device__ __forceinline__ unsigned long long rr_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int trace_begin(int kid) {
+    unsigned long long* p = rr_trace_ptr;
+    if (p == nullptr || (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) != 0) return -1;
+    const int slot = (int)atomicAdd(p, 1ull);
+    if (slot >= (int)p[1]) return -1;
+    p[2 + 4 * slot] = (unsigned long long)kid;
+    p[3 + 4 * slot] = rr_gtimer();
+    return slot;
+}
+// after griddepcontrol.wait returned: the preceding grid has completed and flushed
+__device__ __forceinline__ void trace_dep(int slot) {
+    if (slot >= 0) rr_trace_ptr[4 + 4 * slot] = rr_gtimer();
+}
+__device__ __forceinline__ void trace_end(int slot) {
+    if (slot >= 0) rr_trace_ptr[5 + 4 * slot] = rr_gtimer();
+}
+
 extern int g_use_pdl;   // rr_api.cu; env RR_NO_PDL=1 or rr_set_pdl(0) turns it off
 
 template <typename... KArgs, typename... Args>

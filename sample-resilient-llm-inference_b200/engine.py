@@ -47,7 +47,7 @@ def _p(a: np.ndarray):
 class Engine:
     def __init__(self, weights: Weights, device: int = 0, max_batch: int = 64, ctx_max: int = 1024,
                  max_prefill_tokens: int = 8192, use_cuda_graph: bool = True,
-                 fail_prob: float = 0.0, fail_seed: int = 0):
+                 fail_prob: float = 0.0, fail_seed: int = 0, fuse_silu: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("rr_b200.Engine needs a CUDA device (no CPU fallback)")
         self.spec: ModelSpec = weights.spec
@@ -63,12 +63,24 @@ class Engine:
         def arr(ts):
             return (C.c_void_p * L)(*[t.data_ptr() for t in ts])
 
-        self._arrs = [arr(weights.wqkv), arr(weights.wo), arr(weights.wgu), arr(weights.wdown),
+        # Engine-owned layout of the gate/up weights: rows interleaved in 64-row gate/up blocks so that the GEMM
+        # epilogue can apply SiLU(gate) * up itself (csrc/rr_gemm.cu, OUT_*_SILU).  Needs one gate/up plane at this
+        # batch size (ceil(2*inter/128) >= SM count) and batch tiles >= 32 rows; otherwise the [gate; up] layout is kept.
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+        self.fuse_silu = bool(fuse_silu and s.inter % 64 == 0 and (2 * s.inter + 127) // 128 >= n_sm and max_batch > 16)
+        wgu = weights.wgu
+        if self.fuse_silu:
+            self._wgu_il = []
+            for t in weights.wgu:
+                g, u = t[: s.inter].view(-1, 64, s.hidden), t[s.inter:].view(-1, 64, s.hidden)
+                self._wgu_il.append(torch.stack([g, u], 1).reshape(2 * s.inter, s.hidden).contiguous())
+            wgu = self._wgu_il
+        self._arrs = [arr(weights.wqkv), arr(weights.wo), arr(wgu), arr(weights.wdown),
                       arr(weights.norm_attn), arr(weights.norm_mlp)]
         for t in weights.tensors():
             assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()
         mw = _lib.ModelWeights(weights.embed.data_ptr(), weights.lm_head.data_ptr(),
-                               weights.final_norm.data_ptr(), *self._arrs)
+                               weights.final_norm.data_ptr(), *self._arrs, 1 if self.fuse_silu else 0, 0)
         opts = _lib.EngineOpts(device, max_batch, ctx_max, max_prefill_tokens,
                                1 if use_cuda_graph else 0, fail_seed, fail_prob)
         torch.cuda.synchronize(device)   # weights were produced on torch's stream

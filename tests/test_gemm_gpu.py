@@ -95,3 +95,40 @@ def test_gemm_streamk(rowsA, rowsB, K, bn):
         ref = B.float() @ A.float().t()
         err = (got - ref).abs().max().item()
         assert torch.isfinite(got).all() and err <= 1e-3 * ref.abs().max().item() + 1e-4, (rep, err)
+
+
+def _interleave64(w, inter):
+    g, u = w[:inter].view(-1, 64, w.shape[1]), w[inter:].view(-1, 64, w.shape[1])
+    return torch.stack([g, u], 1).reshape(2 * inter, w.shape[1]).contiguous()
+
+
+@pytest.mark.parametrize("inter,K,B,bn", [(14336, 4096, 64, 64), (1024, 512, 37, 64), (2816, 1024, 20, 32), (1024, 512, 128, 128)])
+def test_gemm_fused_silu_decode_orientation(inter, K, B, bn):
+    from rr_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(inter + B)
+    W = (torch.randn(2 * inter, K, device="cuda", generator=g) * 0.05).bfloat16()        # [gate; up]
+    X = torch.randn(B, K, device="cuda", generator=g).bfloat16()
+    Wil = _interleave64(W, inter)
+    act = torch.full((B, inter), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib.rr_gemm_bf16(Wil.data_ptr(), 2 * inter, K, X.data_ptr(), B, K, K, act.data_ptr(), inter, 0, 1, 2, bn, None))
+    torch.cuda.synchronize()
+    y = X.float() @ W.float().t()
+    ref = torch.nn.functional.silu(y[:, :inter]) * y[:, inter:]
+    assert torch.isfinite(act.float()).all()
+    assert torch.allclose(act.float(), ref, atol=2e-2 * ref.abs().max().item(), rtol=2e-2)
+
+
+@pytest.mark.parametrize("inter,K,T", [(14336, 4096, 1024), (1024, 512, 300), (2816, 1024, 130)])
+def test_gemm_fused_silu_prefill_orientation(inter, K, T):
+    from rr_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(inter + T)
+    W = (torch.randn(2 * inter, K, device="cuda", generator=g) * 0.05).bfloat16()
+    X = torch.randn(T, K, device="cuda", generator=g).bfloat16()
+    Wil = _interleave64(W, inter)
+    act = torch.full((T, inter), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib.rr_gemm_bf16(X.data_ptr(), T, K, Wil.data_ptr(), 2 * inter, K, K, act.data_ptr(), inter, 0, 1, 3, 256, None))
+    torch.cuda.synchronize()
+    y = X.float() @ W.float().t()
+    ref = torch.nn.functional.silu(y[:, :inter]) * y[:, inter:]
+    assert torch.isfinite(act.float()).all()
+    assert torch.allclose(act.float(), ref, atol=2e-2 * ref.abs().max().item(), rtol=2e-2)
