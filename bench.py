@@ -36,6 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "completions/sec (512-in/128-out, Llama-3-8B, 64 concurrent per GPU)"
+# DRAM traffic of one decode step (64 rows, ctx 577) from the committed ncu --set full captures: per layer
+# qkv 50.9 + o 34.1 + gate/up 238.6 + down 122.9 + attention 159.1 MB, x32, + lm_head 1.08 GB (algorithmic: 19.84 GB)
+DECODE_STEP_DRAM_BYTES_NCU = int(32 * (50.91 + 34.12 + 238.55 + 122.92 + 159.14) * 1e6 + 1.083e9)
 
 
 def parse_args():
@@ -130,7 +133,11 @@ def cpu_port_sample(spec, prompt_len, max_new, concurrency, n_gpus, layers_timed
     `decode_steps_timed` of the decode steps are timed and scaled to n_layers / (max_new - 1)."""
     import torch
     from oracle import router as O
-    cores = threads or os.cpu_count() or 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = threads or min(avail, 64)          # beyond ~64 threads the fp32 GEMMs of one request stop scaling
     torch.set_num_threads(cores)
     t0 = time.perf_counter()
     deps = [O.Deployment(group=0, replica=r) for r in range(n_gpus)]
@@ -368,7 +375,9 @@ def main():
                     "api": "Router.completion_batch -> rr_router_process + rr_engine_submit/rr_engine_wait (host buffers)"},
             "gpu_launches": int(sm[5].item() + 2 * K),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": "decode step = 1 CUDA-graph launch (228 kernels with PDL edges; dominant: gemm_bf16_tcgen05<64,*> weight stream)",
+                         "traffic": DECODE_STEP_DRAM_BYTES_NCU if (args.model == "llama-3-8b" and C == 64 and P == 512 and M == 128) else None,
+                         "traffic_source": "sum over the step's kernels of dram__bytes_read+write from ncu --set full (profiles/r01_ncu_full_summary.txt)",
+                         "kernel": "decode step = 1 CUDA-graph launch (228 kernels with PDL edges; dominant: gemm_bf16_tcgen05<64,*> weight stream)",
                          "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms, "peak_source": peak_src},
             "prefill": {"tflops": pf_tflops, "peak_tflops_sustained": tf_peak, "frac": (pf_tflops / tf_peak) if pf_tflops else None,
                         "ms_per_burst": mx[4].item() / K},

@@ -254,6 +254,10 @@ int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int 
                      uint64_t* ticket);
 int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_completion* out,
                    int32_t* tokens_out, int max_tokens_out);
+/* Streaming (SSE): block until the request holds more than `have` tokens, is done, or `timeout_s` elapses;
+ * copies the tokens generated so far.  Does not consume the request — finish with rr_engine_wait. */
+int rr_engine_peek(rr_engine* e, uint64_t ticket, int have, double timeout_s, int32_t* tokens_out,
+                   int max_tokens_out, int32_t* n_generated, int32_t* done, double* t_first_token_s);
 /* Closed-batch convenience used by bench.py: submit all, wait all. prompts are host buffers
  * (pinned or pageable); the H2D copies happen inside. */
 int rr_engine_run_batch(rr_engine* e, const int32_t* prompt_ids, const int32_t* prompt_start,

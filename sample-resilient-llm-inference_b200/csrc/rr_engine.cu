@@ -685,6 +685,31 @@ RR_API int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_promp
     return RR_OK;
 }
 
+// Streaming support: block until the request has more than `have` tokens (or is done / the wait times out), then
+// copy the tokens generated so far.  Does not consume the request; finish with rr_engine_wait.
+RR_API int rr_engine_peek(rr_engine* e, uint64_t ticket, int have, double timeout_s, int32_t* tokens_out,
+                          int max_tokens_out, int32_t* n_generated, int32_t* done, double* t_first_token_s) {
+    if (!e || !n_generated || !done) return RR_INVALID_ARGUMENT;
+    std::unique_lock<std::mutex> lk(e->mu);
+    auto it = e->table.find(ticket);
+    if (it == e->table.end()) return RR_INVALID_ARGUMENT;
+    Request* r = it->second;
+    const auto deadline = std::chrono::steady_clock::now() +
+                          std::chrono::duration<double>(timeout_s > 0 ? timeout_s : 1e9);
+    while (!r->done && (int)r->out.size() <= have) {
+        if (e->cv_done.wait_until(lk, deadline) == std::cv_status::timeout) break;
+    }
+    const int n = (int)r->out.size();
+    *n_generated = n;
+    *done = r->done ? 1 : 0;
+    if (t_first_token_s) *t_first_token_s = r->t_first - r->t_submit;
+    if (tokens_out) {
+        const int m = n < max_tokens_out ? n : max_tokens_out;
+        memcpy(tokens_out, r->out.data(), sizeof(int32_t) * m);
+    }
+    return RR_OK;
+}
+
 RR_API int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_completion* out, int32_t* tokens_out,
                           int max_tokens_out) {
     if (!e || !out) return RR_INVALID_ARGUMENT;

@@ -143,6 +143,14 @@ class Engine:
         return CompletionRecord(ticket, rc, c.n_prompt, buf[:c.n_generated].tolist(), c.t_submit_s,
                                 c.t_first_token_s, c.t_done_s)
 
+    def peek(self, ticket: int, have: int, timeout: float = 0.05, max_tokens: int = 4096):
+        """Streaming: wait until more than `have` tokens exist (or done / timeout). -> (tokens so far, done, ttft_s)."""
+        buf = np.zeros(max_tokens, dtype=np.int32)
+        n, done, ttft = C.c_int32(), C.c_int32(), C.c_double()
+        _lib.check(_lib.lib.rr_engine_peek(self._h, ticket, have, float(timeout), _p(buf), max_tokens, C.byref(n),
+                                           C.byref(done), C.byref(ttft)), "rr_engine_peek")
+        return buf[: n.value].tolist(), bool(done.value), ttft.value
+
     def run_batch(self, prompt_ids: np.ndarray, prompt_start: np.ndarray, max_new_tokens: int):
         """Closed burst: submit every prompt, wait for all.  `prompt_ids` is a host buffer; the
         H2D copies happen inside the library.  -> (completions, tokens [n, max_new])."""

@@ -152,11 +152,18 @@ class StubBackend:
         now = time.perf_counter()
         return (7 if failed else 0), ([] if failed else [3 + (i % 200) for i in range(n)]), now - t, now - t
 
+    def peek(self, handle, have, timeout=0.05):
+        failed, n, t = handle
+        return ([] if failed else [3 + (i % 200) for i in range(n)]), True, time.perf_counter() - t
+
 
 class EngineBackend:
     def __init__(self, engine):
         self.engine = engine
         self.vocab = engine.spec.vocab
+
+    def peek(self, handle, have, timeout=0.05):
+        return self.engine.peek(handle, have, timeout=timeout)
 
     def submit(self, prompt_ids, max_new):
         return self.engine.submit(prompt_ids, max_new)
@@ -291,6 +298,46 @@ class Router:
             if st == 6:
                 raise APITimeoutError(f"Request timed out after {timeout}s")
             last_err = APIError(f"backend failure on deployment {dep} ({self.cfg.deployments[dep].model})")
+            chain_start = pos + 1
+
+    def completion_stream(self, model: str, messages: Optional[Sequence[dict]] = None, timeout: Optional[float] = None,
+                          max_tokens: Optional[int] = None, prompt_ids: Optional[Sequence[int]] = None):
+        """Streaming variant (SSE in server.py): admission exactly like completion(); yields
+        (model_label, new_token_ids, done, ttft_s) as tokens arrive.  A backend failure before the first token walks the
+        fallback chain; rate limiting raises RateLimitError before anything is yielded."""
+        g = self.cfg.group_index(model)
+        if g < 0:
+            raise BadRequestError(f"Invalid model name passed in model={model}")
+        if prompt_ids is None:
+            prompt_ids = tokenize(messages_to_text(messages or []), self._vocab())
+        max_new = max_tokens or self.default_max_tokens
+        chain_start = 0
+        while True:
+            (status, dep, sg, pos), = self.process([(EV_ADMIT, g, len(prompt_ids), chain_start, self.now_ms())])
+            if status == 1:
+                raise RateLimitError(f"No deployments available for selected model, passed model={model} (rate limited)")
+            if status != 0:
+                raise BadRequestError(f"Invalid model name passed in model={model}")
+            backend = self._backend_for(dep)
+            label = self.cfg.deployments[dep].response_model
+            h = backend.submit(prompt_ids, max_new)
+            sent, failed = 0, False
+            while True:
+                toks, done, ttft = backend.peek(h, sent)
+                if len(toks) > sent:
+                    yield label, toks[sent:], False, ttft
+                    sent = len(toks)
+                if done:
+                    st, toks, ttft, _lat = backend.wait(h, timeout)
+                    failed = st != 0
+                    break
+            if not failed:
+                self.process([(EV_DONE, dep, sent, 0, self.now_ms())])
+                yield label, [], True, ttft
+                return
+            self.process([(EV_FAIL, dep, 0, 0, self.now_ms())])
+            if sent > 0:
+                raise APIError(f"backend failure on deployment {dep} after {sent} tokens")
             chain_start = pos + 1
 
     def completion_batch(self, model: str, prompts: Sequence[Sequence[int]], max_tokens: int,

@@ -31,6 +31,40 @@ def create_app(router: Router):
     app = FastAPI(title="rr_b200 gateway")
     t_start = time.time()
 
+    async def stream_completion(model, messages, body):
+        """Server-sent events in the OpenAI chunk format; the first chunk leaves when the first token exists (TTFT)."""
+        import json as _json
+        import uuid
+        from fastapi.responses import StreamingResponse
+        from .router import detokenize
+        gen = router.completion_stream(model=model, messages=messages, timeout=body.get("timeout"),
+                                       max_tokens=body.get("max_tokens"))
+        try:
+            first = await run_in_threadpool(next, gen)            # admission errors surface before the 200
+        except RateLimitError as e:
+            return JSONResponse(_error_body(e, "rate_limit_error"), 429, headers={"retry-after": "1"})
+        except BadRequestError as e:
+            return JSONResponse(_error_body(e, "invalid_request_error"), 400)
+        except APIError as e:
+            return JSONResponse(_error_body(e, "api_error"), e.status_code)
+        cid = "chatcmpl-" + uuid.uuid4().hex[:24]
+
+        def chunk(label, toks, done):
+            delta = {} if done else {"role": "assistant", "content": detokenize(toks)}
+            return "data: " + _json.dumps({"id": cid, "object": "chat.completion.chunk", "created": int(time.time()),
+                                           "model": label, "choices": [{"index": 0, "delta": delta,
+                                                                        "finish_reason": "length" if done else None}]}) + "\n\n"
+
+        def events():
+            label, toks, done, _ = first
+            yield chunk(label, toks, done)
+            if not done:
+                for label, toks, done, _ in gen:
+                    yield chunk(label, toks, done)
+            yield "data: [DONE]\n\n"
+
+        return StreamingResponse(events(), media_type="text/event-stream")
+
     async def chat_completions(request: Request):
         try:
             body = await request.json()
@@ -40,6 +74,8 @@ def create_app(router: Router):
         if not isinstance(model, str) or not isinstance(messages, list):
             return JSONResponse(_error_body(BadRequestError("`model` and `messages` are required"),
                                             "invalid_request_error"), 400)
+        if body.get("stream"):
+            return await stream_completion(model, messages, body)
         try:
             resp = await run_in_threadpool(router.completion, model=model, messages=messages,
                                            timeout=body.get("timeout"), max_tokens=body.get("max_tokens"))

@@ -156,3 +156,42 @@ def test_demo_drivers_in_process(capsys, monkeypatch):
     assert res["ok"] == 10 and sorted(res["distribution"].values()) == [3, 3, 4]
     q = demo_quota_isolation.main()
     assert q == {"A": (3, 2), "B": (5, 0), "C": (5, 0)}
+
+
+def test_streaming_over_http_with_real_replica():
+    """SSE through the OpenAI SDK against an engine-backed router: chunks arrive, concatenate to the non-streamed
+    completion, and admission errors still map to 429."""
+    import openai
+    import uvicorn
+    from rr_b200 import Engine, EngineBackend, Router, SPECS, make_weights
+    from rr_b200.server import create_app
+    w = make_weights(SPECS["tiny"], seed=4, sigma=0.05, device="cuda")
+    eng = Engine(w, max_batch=8, ctx_max=256, max_prefill_tokens=512)
+    ml = [{"model_name": "chat", "litellm_params": {"model": "b200/tiny@stream", "gpu": 0}, "rpm": 3}]
+    r = Router(model_list=ml, enable_pre_call_checks=True, backends={0: EngineBackend(eng)}, default_max_tokens=24)
+    port = 19000 + os.getpid() % 1000
+    server = uvicorn.Server(uvicorn.Config(create_app(r), host="127.0.0.1", port=port, log_level="error"))
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    for _ in range(100):
+        if server.started:
+            break
+        time.sleep(0.05)
+    try:
+        client = openai.OpenAI(api_key="k", base_url=f"http://127.0.0.1:{port}", max_retries=0)
+        msgs = [{"role": "user", "content": "stream me"}]
+        full = client.chat.completions.create(model="chat", messages=msgs, timeout=30)
+        parts, n_chunks = [], 0
+        for ch in client.chat.completions.create(model="chat", messages=msgs, timeout=30, stream=True):
+            n_chunks += 1
+            assert ch.model == "tiny@stream"
+            parts.append(ch.choices[0].delta.content or "")
+        assert n_chunks >= 3 and "".join(parts) == full.choices[0].message.content
+        direct = list(r.completion_stream(model="chat", messages=msgs))
+        assert direct[-1][2] is True and sum(len(t) for _, t, _, _ in direct) == 24
+        with pytest.raises(openai.RateLimitError):
+            client.chat.completions.create(model="chat", messages=msgs, timeout=30, stream=True)   # rpm 3 used up
+    finally:
+        server.should_exit = True
+        th.join(10)
+        eng.close(); r.close()

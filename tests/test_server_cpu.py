@@ -49,3 +49,23 @@ def test_routes_and_status_codes():
 def test_text_helpers():
     assert messages_to_text([{"role": "user", "content": "hi"}, {"role": "assistant", "content": "yo"}]) == "user: hi\nassistant: yo"
     assert detokenize([1, 3 + ord("o"), 3 + ord("k")]) == "ok"
+
+
+def test_sse_stream_with_fake_router():
+    class R(_FakeRouter):
+        def completion_stream(self, model, messages, timeout=None, max_tokens=None):
+            if model == "limited":
+                raise RateLimitError("No deployments available")
+            yield "llama-3-8b@x", [3 + ord("h")], False, 0.01
+            yield "llama-3-8b@x", [3 + ord("i")], False, 0.01
+            yield "llama-3-8b@x", [], True, 0.01
+    c = TestClient(create_app(R()))
+    r = c.post("/chat/completions", json={"model": "g", "messages": [{"role": "user", "content": "x"}], "stream": True})
+    assert r.status_code == 200 and r.headers["content-type"].startswith("text/event-stream")
+    lines = [ln[6:] for ln in r.text.splitlines() if ln.startswith("data: ")]
+    assert lines[-1] == "[DONE]"
+    import json
+    chunks = [json.loads(x) for x in lines[:-1]]
+    assert "".join(ch["choices"][0]["delta"].get("content", "") for ch in chunks) == "hi"
+    assert chunks[-1]["choices"][0]["finish_reason"] == "length" and chunks[0]["model"] == "llama-3-8b@x"
+    assert c.post("/chat/completions", json={"model": "limited", "messages": [], "stream": True}).status_code == 429
