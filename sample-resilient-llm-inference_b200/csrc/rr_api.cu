@@ -165,7 +165,7 @@ RR_API int rr_op_rope_kv(const void* qkv, int is_bf16, int n_splits, long long s
     a.qkv = mk_part(qkv, is_bf16, n_splits, split_stride, ld);
     a.q_out = (__nv_bfloat16*)q_out; a.k_cache = (__nv_bfloat16*)k_cache; a.v_cache = (__nv_bfloat16*)v_cache;
     a.slot = slot; a.pos = pos; a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads;
-    a.ctx_max = ctx_max; a.theta = theta; a.table = nullptr;
+    a.ctx_max = ctx_max; a.theta = theta; a.table = nullptr; a.head_dim = 128;
     launch_rope_kv(a, (cudaStream_t)stream);
     return check_last();
 }
@@ -190,7 +190,7 @@ RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_c
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.slot = slot; a.pos = pos;
     a.rows = rows; a.n_heads = n_heads; a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
     a.kv_splits = kv_splits < 1 ? 1 : kv_splits; a.ws = nullptr;
-    a.fuse_rope = 0; a.qkv.ptr = nullptr; a.rope_table = nullptr;
+    a.fuse_rope = 0; a.qkv.ptr = nullptr; a.rope_table = nullptr; a.head_dim = 128;
     { int rcm = decode_attn_make_maps(&a, n_slots); if (rcm != RR_OK) return rcm; }
     float* ws = nullptr;
     if (a.kv_splits > 1) {
@@ -213,7 +213,7 @@ RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_
     a.q = (const __nv_bfloat16*)q; a.k_cache = (const __nv_bfloat16*)k_cache;
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.seq_start = seq_start;
     a.seq_slot = seq_slot; a.n_seqs = n_seqs; a.max_len = max_len; a.n_heads = n_heads;
-    a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale;
+    a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale; a.head_dim = 128;
     launch_prefill_attn(a, (cudaStream_t)stream);
     return check_last();
 }

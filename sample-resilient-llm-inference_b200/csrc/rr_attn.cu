@@ -194,11 +194,12 @@ prefill_attn_kernel(PrefillAttnArgs a) {
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) {
         const int d = nt * 8 + t * 2;
+        if (d >= a.head_dim) break;                 // columns beyond the true head dim are zero padding
         if (qi0 < len)
-            *reinterpret_cast<uint32_t*>(a.out + (size_t)(tok0 + qi0) * a.n_heads * HD + head * HD + d) =
+            *reinterpret_cast<uint32_t*>(a.out + (size_t)(tok0 + qi0) * a.n_heads * a.head_dim + head * a.head_dim + d) =
                 pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
         if (qi1 < len)
-            *reinterpret_cast<uint32_t*>(a.out + (size_t)(tok0 + qi1) * a.n_heads * HD + head * HD + d) =
+            *reinterpret_cast<uint32_t*>(a.out + (size_t)(tok0 + qi1) * a.n_heads * a.head_dim + head * a.head_dim + d) =
                 pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
     }
     trace_end(tr_slot);

@@ -111,9 +111,12 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             // every head); if this CTA holds token `pos`: rotate the new key, append k / v (bf16) to the cache and
             // publish the row in smem.  All loads of one split plane are issued together (one latency per plane);
             // the whole block overlaps the flight of the first K/V tiles.
+            const int hd = a.head_dim, half = hd >> 1;
             const int i = 2 * lane;
-            const int kcol = a.n_heads * HD + kvh * HD, vcol = (a.n_heads + a.n_kv_heads) * HD + kvh * HD;
-            const float4 cs = *reinterpret_cast<const float4*>(a.rope_table + (size_t)pos * 64 + i);
+            const bool lane_on = i < half;                            // rotation pairs (i, i + hd/2)
+            const bool v_on = 4 * lane < hd;
+            const int kcol = a.n_heads * hd + kvh * hd, vcol = (a.n_heads + a.n_kv_heads) * hd + kvh * hd;
+            const float4 cs = *reinterpret_cast<const float4*>(a.rope_table + (size_t)pos * 64 + (lane_on ? i : 0));
             float2 lo[G], hi[G];
             float2 klo = make_float2(0.f, 0.f), khi = klo, v0 = klo, v1 = klo;
 #pragma unroll
@@ -121,18 +124,23 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             for (int z = 0; z < a.qkv.n_splits; ++z) {
                 const float* pl = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)z * a.qkv.split_stride +
                                   (size_t)row * a.qkv.ld;
+                const float2 z2 = make_float2(0.f, 0.f);
                 float2 tl[G], th[G];
 #pragma unroll
                 for (int h = 0; h < G; ++h) {
-                    tl[h] = *reinterpret_cast<const float2*>(pl + (kvh * G + h) * HD + i);
-                    th[h] = *reinterpret_cast<const float2*>(pl + (kvh * G + h) * HD + 64 + i);
+                    tl[h] = lane_on ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + i) : z2;
+                    th[h] = lane_on ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + half + i) : z2;
                 }
-                float2 t0 = klo, t1 = klo, t2 = klo, t3 = klo;
+                float2 t0 = z2, t1 = z2, t2 = z2, t3 = z2;
                 if (owns_new) {
-                    t0 = *reinterpret_cast<const float2*>(pl + kcol + i);
-                    t1 = *reinterpret_cast<const float2*>(pl + kcol + 64 + i);
-                    t2 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane);
-                    t3 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane + 2);
+                    if (lane_on) {
+                        t0 = *reinterpret_cast<const float2*>(pl + kcol + i);
+                        t1 = *reinterpret_cast<const float2*>(pl + kcol + half + i);
+                    }
+                    if (v_on) {
+                        t2 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane);
+                        t3 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane + 2);
+                    }
                 }
 #pragma unroll
                 for (int h = 0; h < G; ++h) { lo[h].x += tl[h].x; lo[h].y += tl[h].y; hi[h].x += th[h].x; hi[h].y += th[h].y; }
@@ -141,12 +149,22 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
                     v0.x += t2.x; v0.y += t2.y; v1.x += t3.x; v1.y += t3.y;
                 }
             }
+            // smem rows are 128 wide: zero the padding beyond the true head dim first
+            if (hd < HD) {
 #pragma unroll
-            for (int h = 0; h < G; ++h) {
-                *reinterpret_cast<uint32_t*>(q_s + h * HD + i) =
-                    pack_bf16(lo[h].x * cs.x - hi[h].x * cs.y, lo[h].y * cs.z - hi[h].y * cs.w);
-                *reinterpret_cast<uint32_t*>(q_s + h * HD + 64 + i) =
-                    pack_bf16(hi[h].x * cs.x + lo[h].x * cs.y, hi[h].y * cs.z + lo[h].y * cs.w);
+                for (int h = 0; h < G; ++h) *reinterpret_cast<uint2*>(q_s + h * HD + 4 * lane) = make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(newkv + 4 * lane) = make_uint2(0u, 0u);
+                *reinterpret_cast<uint2*>(newkv + HD + 4 * lane) = make_uint2(0u, 0u);
+                __syncwarp();
+            }
+            if (lane_on) {
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    *reinterpret_cast<uint32_t*>(q_s + h * HD + i) =
+                        pack_bf16(lo[h].x * cs.x - hi[h].x * cs.y, lo[h].y * cs.z - hi[h].y * cs.w);
+                    *reinterpret_cast<uint32_t*>(q_s + h * HD + half + i) =
+                        pack_bf16(hi[h].x * cs.x + lo[h].x * cs.y, hi[h].y * cs.z + lo[h].y * cs.w);
+                }
             }
             if (owns_new) {
                 const uint32_t k_lo = pack_bf16(klo.x * cs.x - khi.x * cs.y, klo.y * cs.z - khi.y * cs.w);
@@ -156,12 +174,16 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
                 vv.y = pack_bf16(v1.x, v1.y);
                 __nv_bfloat16* kdst = const_cast<__nv_bfloat16*>(a.k_cache) + ((size_t)row_base + pos) * HD;
                 __nv_bfloat16* vdst = const_cast<__nv_bfloat16*>(a.v_cache) + ((size_t)row_base + pos) * HD;
-                *reinterpret_cast<uint32_t*>(kdst + i) = k_lo;
-                *reinterpret_cast<uint32_t*>(kdst + 64 + i) = k_hi;
-                *reinterpret_cast<uint2*>(vdst + 4 * lane) = vv;
-                *reinterpret_cast<uint32_t*>(newkv + i) = k_lo;
-                *reinterpret_cast<uint32_t*>(newkv + 64 + i) = k_hi;
-                *reinterpret_cast<uint2*>(newkv + HD + 4 * lane) = vv;
+                if (lane_on) {
+                    *reinterpret_cast<uint32_t*>(kdst + i) = k_lo;
+                    *reinterpret_cast<uint32_t*>(kdst + half + i) = k_hi;
+                    *reinterpret_cast<uint32_t*>(newkv + i) = k_lo;
+                    *reinterpret_cast<uint32_t*>(newkv + half + i) = k_hi;
+                }
+                if (v_on) {
+                    *reinterpret_cast<uint2*>(vdst + 4 * lane) = vv;
+                    *reinterpret_cast<uint2*>(newkv + HD + 4 * lane) = vv;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(newkv_bar);      // q (and the new k / v row) are in smem
@@ -293,6 +315,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int i = tid; i < G * (HD / 2); i += 128) {
         const int h = i / (HD / 2), dp = (i % (HD / 2)) * 2;
+        if (dp >= a.head_dim) continue;                 // padding columns
         float M = -INFINITY;
 #pragma unroll
         for (int w = 0; w < 4; ++w) M = fmaxf(M, red_ml[(w * 8 + h) * 2]);
@@ -308,7 +331,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
         const int head = kvh * G + h;
         if (a.kv_splits == 1) {
             const float inv = L > 0.f ? 1.f / L : 0.f;
-            *reinterpret_cast<uint32_t*>(a.out + (size_t)row * a.n_heads * HD + head * HD + dp) =
+            *reinterpret_cast<uint32_t*>(a.out + (size_t)row * a.n_heads * a.head_dim + head * a.head_dim + dp) =
                 pack_bf16(o0 * inv, o1 * inv);
         } else {
             float* w = a.ws + (((size_t)row * a.n_heads + head) * a.kv_splits + split) * (HD + 2);
@@ -322,7 +345,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
 
 // combine split-KV partials: grid (n_heads, rows), 64 threads (dim pairs)
 __global__ void decode_attn_combine_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ out,
-                                           const int32_t* __restrict__ slot, int n_heads, int kv_splits) {
+                                           const int32_t* __restrict__ slot, int n_heads, int kv_splits, int head_dim) {
     griddep_launch();
     griddep_wait();
     const int head = blockIdx.x, row = blockIdx.y;
@@ -332,6 +355,7 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ ws, __nv_bf
     for (int s = 0; s < kv_splits; ++s) m = fmaxf(m, w[s * (HD + 2) + HD]);
     float l = 0.f, o0 = 0.f, o1 = 0.f;
     const int dp = threadIdx.x;
+    if (dp * 2 >= head_dim) return;
     for (int s = 0; s < kv_splits; ++s) {
         const float* p = w + s * (HD + 2);
         const float ms = p[HD];
@@ -342,7 +366,7 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ ws, __nv_bf
         o1 += p[dp * 2 + 1] * f;
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    *reinterpret_cast<uint32_t*>(out + (size_t)row * n_heads * HD + head * HD + dp * 2) = pack_bf16(o0 * inv, o1 * inv);
+    *reinterpret_cast<uint32_t*>(out + (size_t)row * n_heads * head_dim + head * head_dim + dp * 2) = pack_bf16(o0 * inv, o1 * inv);
 }
 
 size_t decode_attn_ws_bytes(int rows, int n_heads, int kv_splits) {
@@ -368,7 +392,7 @@ static void launch_dec(const DecodeAttnArgs& a, cudaStream_t st) {
     launch_pdl(decode_attn_mma_kernel<G>, grid, dim3(DEC_THREADS), (size_t)DEC_SMEM, st, a);
     if (a.kv_splits > 1)
         launch_pdl(decode_attn_combine_kernel, dim3(a.n_heads, a.rows), dim3(64), 0, st, (const float*)a.ws, a.out,
-                   a.slot, a.n_heads, a.kv_splits);
+                   a.slot, a.n_heads, a.kv_splits, a.head_dim);
 }
 
 void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st) {

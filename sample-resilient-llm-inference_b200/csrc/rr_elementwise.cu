@@ -164,19 +164,20 @@ void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStr
 // head_dim = 128, HF "rotate_half" convention: pairs (i, i + 64), inv_freq_i = theta^(-i/64).
 // cos/sin come from a table [ctx_max][64] (float2) built once per engine in double precision;
 // without a table (kernel-level tests) they are computed inline.
-__global__ void rope_table_kernel(float2* __restrict__ table, int ctx_max, double theta) {
+__global__ void rope_table_kernel(float2* __restrict__ table, int ctx_max, double theta, int half) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= ctx_max * 64) return;
     const int pos = idx >> 6, i = idx & 63;
-    const double inv_freq = pow(theta, -(double)i / 64.0);
+    if (i >= half) { table[idx] = make_float2(1.f, 0.f); return; }
+    const double inv_freq = pow(theta, -(double)i / (double)half);
     // the oracle (and HF) form the angle in fp32: pos * float(inv_freq)
     const float ang = (float)pos * (float)inv_freq;
     table[idx] = make_float2((float)cos((double)ang), (float)sin((double)ang));
 }
 
-void launch_rope_table(float2* table, int ctx_max, float theta, cudaStream_t st) {
+void launch_rope_table(float2* table, int ctx_max, float theta, int head_dim, cudaStream_t st) {
     const int n = ctx_max * 64;
-    rope_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, ctx_max, (double)theta);
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, ctx_max, (double)theta, head_dim / 2);
 }
 
 __device__ __forceinline__ float2 part_load2(const PartIn& p, int row, int col) {   // 2 consecutive columns
@@ -204,25 +205,27 @@ rope_kv_kernel(RopeArgs a) {
     const int slot = a.slot[row];
     if (slot < 0) return;
     const int pos = a.pos[row];
-    // work items of 2 rotation pairs: (head, i..i+1) for q heads then k heads, then v copies (4 elements)
-    const int n_q = a.n_heads * 32, n_k = a.n_kv_heads * 32;
-    const int total = n_q + n_k + n_k;
+    // work items of 2 rotation pairs: (head, i..i+1) for q heads then k heads, then v copies (4 elements).
+    // hd = true head dim: rotation pairs (i, i + hd/2); destination rows are padded to 128 (pad stays zero).
+    const int hd = a.head_dim, half = hd >> 1, ipw = half >> 1, vpw = hd >> 2;      // items per head
+    const int n_q = a.n_heads * ipw, n_k = a.n_kv_heads * ipw;
+    const int total = n_q + n_k + a.n_kv_heads * vpw;
     const float l2t = a.table ? 0.f : log2f(a.theta);
     for (int it = threadIdx.x; it < total; it += blockDim.x) {
         if (it < n_q + n_k) {
             const bool is_q = it < n_q;
             const int j = is_q ? it : it - n_q;
-            const int head = j >> 5, i = (j & 31) * 2;
-            const int col = (is_q ? 0 : a.n_heads * 128) + head * 128 + i;
+            const int head = j / ipw, i = (j % ipw) * 2;
+            const int col = (is_q ? 0 : a.n_heads * hd) + head * hd + i;
             const float2 lo = part_load2(a.qkv, row, col);
-            const float2 hi = part_load2(a.qkv, row, col + 64);
+            const float2 hi = part_load2(a.qkv, row, col + half);
             float c0, s0, c1, s1;
             if (a.table) {
                 const float4 t = *reinterpret_cast<const float4*>(a.table + (size_t)pos * 64 + i);
                 c0 = t.x; s0 = t.y; c1 = t.z; s1 = t.w;
             } else {
-                sincosf((float)pos * exp2f(-l2t * (float)i * (1.f / 64.f)), &s0, &c0);
-                sincosf((float)pos * exp2f(-l2t * (float)(i + 1) * (1.f / 64.f)), &s1, &c1);
+                sincosf((float)pos * exp2f(-l2t * (float)i / (float)half), &s0, &c0);
+                sincosf((float)pos * exp2f(-l2t * (float)(i + 1) / (float)half), &s1, &c1);
             }
             const uint32_t o_lo = pack_bf16(lo.x * c0 - hi.x * s0, lo.y * c1 - hi.y * s1);
             const uint32_t o_hi = pack_bf16(hi.x * c0 + lo.x * s0, hi.y * c1 + lo.y * s1);
@@ -230,11 +233,11 @@ rope_kv_kernel(RopeArgs a) {
                 ? a.q_out + (size_t)row * (a.n_heads * 128) + head * 128 + i
                 : a.k_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i;
             *reinterpret_cast<uint32_t*>(dst) = o_lo;
-            *reinterpret_cast<uint32_t*>(dst + 64) = o_hi;
+            *reinterpret_cast<uint32_t*>(dst + half) = o_hi;
         } else {
-            const int j = it - n_q - n_k;            // [0, n_kv*32): 4 elements each
-            const int head = j >> 5, i4 = (j & 31) * 4;
-            const int col = (a.n_heads + a.n_kv_heads) * 128 + head * 128 + i4;
+            const int j = it - n_q - n_k;            // 4 elements each
+            const int head = j / vpw, i4 = (j % vpw) * 4;
+            const int col = (a.n_heads + a.n_kv_heads) * hd + head * hd + i4;
             const float4 v = part_load4(a.qkv, row, col);
             __nv_bfloat16* dst = a.v_cache + (((size_t)slot * a.n_kv_heads + head) * a.ctx_max + pos) * 128 + i4;
             uint2 o;

@@ -314,12 +314,12 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         ra.qkv = part_bf16(e->pqkv, e->nqkv);
         ra.q_out = e->pq; ra.k_cache = kc; ra.v_cache = vc; ra.slot = p_slt; ra.pos = p_pos; ra.rows = T;
         ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max; ra.theta = d.rope_theta;
-        ra.table = e->rope_table;
+        ra.table = e->rope_table; ra.head_dim = d.head_dim;
         launch_rope_kv(ra, s); ++nl;
         PrefillAttnArgs pa;
         pa.q = e->pq; pa.k_cache = kc; pa.v_cache = vc; pa.out = e->pattn; pa.seq_start = p_ss; pa.seq_slot = p_sl;
         pa.n_seqs = n_seqs; pa.max_len = max_len; pa.n_heads = d.n_heads; pa.n_kv_heads = d.n_kv_heads;
-        pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim);
+        pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim); pa.head_dim = d.head_dim;
         launch_prefill_attn(pa, s); ++nl;
         if (gemm_launch(P->o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
@@ -469,7 +469,9 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                             rr_engine** out) {
     if (!desc || !w || !opts || !out) return RR_INVALID_ARGUMENT;
     const rr_model_desc& d = *desc;
-    if (d.head_dim != 128 || d.n_heads % d.n_kv_heads || d.hidden % 64 || d.inter % 64 || d.n_layers < 1)
+    // head_dim: 64..128, multiple of 16; attention operands (q, KV cache rows) are zero-padded to 128
+    if (d.head_dim < 64 || d.head_dim > 128 || d.head_dim % 16 || d.n_heads % d.n_kv_heads || d.hidden % 64 ||
+        d.inter % 64 || d.n_layers < 1)
         return RR_INVALID_ARGUMENT;
     const int G = d.n_heads / d.n_kv_heads;
     if (!(G == 1 || G == 2 || G == 4 || G == 8)) return RR_INVALID_ARGUMENT;
@@ -481,7 +483,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     e->d = d; e->o = *opts;
     e->Bm = opts->max_batch;
     e->bn_dec = pick_bn(e->Bm);
-    e->nq = d.n_heads * 128; e->nkv_dim = d.n_kv_heads * 128; e->nqkv = e->nq + 2 * e->nkv_dim;
+    e->nq = d.n_heads * d.head_dim; e->nkv_dim = d.n_kv_heads * d.head_dim; e->nqkv = e->nq + 2 * e->nkv_dim;
     e->Tmax = opts->max_prefill_tokens > 0 ? opts->max_prefill_tokens : 8192;
     if (e->Tmax < 16) e->Tmax = 16;
     e->embed = w->embed; e->lm_head = w->lm_head; e->final_norm = w->final_norm;
@@ -510,7 +512,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRYC(cudaMemset(e->d_slot, 0xff, sizeof(int32_t) * B));
     TRY(dalloc(e, &e->x, (size_t)B * d.hidden));
     TRY(dalloc(e, &e->xn, (size_t)B * d.hidden));
-    TRY(dalloc(e, &e->qbuf, (size_t)B * e->nq));
+    TRY(dalloc(e, &e->qbuf, (size_t)B * d.n_heads * 128));
     TRY(dalloc(e, &e->attn_out, (size_t)B * e->nq));
     TRY(dalloc(e, &e->act, (size_t)B * d.inter));
     TRY(dalloc(e, &e->part_qkv, (size_t)e->s_qkv * B * e->nqkv));
@@ -520,7 +522,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRY(dalloc(e, &e->logits, (size_t)B * d.vocab));
     TRY(dalloc(e, &e->xn_last, (size_t)B * d.hidden));
     TRY(dalloc(e, &e->rope_table, (size_t)opts->ctx_max * 64));
-    launch_rope_table(e->rope_table, opts->ctx_max, d.rope_theta, e->stream);
+    launch_rope_table(e->rope_table, opts->ctx_max, d.rope_theta, d.head_dim, e->stream);
     e->kv_layer_stride = (size_t)B * d.n_kv_heads * opts->ctx_max * 128;
     TRY(dalloc(e, &e->kcache, e->kv_layer_stride * L));
     TRY(dalloc(e, &e->vcache, e->kv_layer_stride * L));
@@ -538,7 +540,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRY(dalloc(e, &e->px, (size_t)T * d.hidden, false));
     TRY(dalloc(e, &e->pxn, (size_t)T * d.hidden, false));
     TRY(dalloc(e, &e->pqkv, (size_t)T * e->nqkv, false));
-    TRY(dalloc(e, &e->pq, (size_t)T * e->nq, false));
+    TRY(dalloc(e, &e->pq, (size_t)T * d.n_heads * 128));                 // zeroed: columns beyond head_dim stay 0
     TRY(dalloc(e, &e->pattn, (size_t)T * e->nq, false));
     TRY(dalloc(e, &e->po, (size_t)T * d.hidden, false));
     TRY(dalloc(e, &e->pgu, (size_t)T * 2 * d.inter, false));
@@ -557,6 +559,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         da.ctx_max = opts->ctx_max; da.scale = 1.0f / sqrtf((float)d.head_dim); da.ws = e->attn_ws;
         da.kv_splits = e->kv_splits;
         da.fuse_rope = 1; da.qkv = part_f32(e->part_qkv, e->s_qkv, B, e->nqkv); da.rope_table = e->rope_table;
+        da.head_dim = d.head_dim;
         TRY(decode_attn_make_maps(&da, B));
         TRY(gemm_plan_init(&e->pl_qkv[l], e->wqkv[l], e->nqkv, d.hidden, e->xn, B, d.hidden, d.hidden, e->part_qkv,
                            e->nqkv, B, e->s_qkv, OUT_TRANSPOSED_F32, e->bn_dec));

@@ -58,9 +58,10 @@ struct RopeArgs {
     int rows, n_heads, n_kv_heads, ctx_max;
     float theta;
     const float2* table;      // [ctx_max][64] (cos, sin) or null: compute inline
+    int head_dim;             // true head dim (<= 128, % 8 == 0): column stride inside qkv; q_out / caches are padded to 128
 };
 void launch_rope_kv(const RopeArgs& a, cudaStream_t st);
-void launch_rope_table(float2* table, int ctx_max, float theta, cudaStream_t st);
+void launch_rope_table(float2* table, int ctx_max, float theta, int head_dim, cudaStream_t st);
 // argmax over fp32 logits [rows, vocab] (partials with n_splits = 1); writes next token, and if
 // advance != 0: pos[row]++ (decode bookkeeping folded into the same launch).
 void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
@@ -85,6 +86,7 @@ struct DecodeAttnArgs {
     int fuse_rope;
     PartIn qkv;
     const float2* rope_table;
+    int head_dim;             // true head dim: qkv column stride and `out` head stride; q / caches padded to 128
 };
 int decode_attn_make_maps(DecodeAttnArgs* a, int n_slots);   // fills tmK / tmV (ctx_max % 64 == 0)
 void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st);
@@ -99,6 +101,7 @@ struct PrefillAttnArgs {
     const int32_t* seq_slot;  // [n_seqs]
     int n_seqs, max_len, n_heads, n_kv_heads, ctx_max;
     float scale;
+    int head_dim;             // true head dim: `out` head stride; q / caches padded to 128
 };
 void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st);
 

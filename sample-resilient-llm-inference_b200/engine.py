@@ -65,9 +65,13 @@ class Engine:
 
         # Engine-owned layout of the gate/up weights: rows interleaved in 64-row gate/up blocks so that the GEMM
         # epilogue can apply SiLU(gate) * up itself (csrc/rr_gemm.cu, OUT_*_SILU).  Needs one gate/up plane at this
-        # batch size (ceil(2*inter/128) >= SM count) and batch tiles >= 32 rows; otherwise the [gate; up] layout is kept.
+        # batch size (no split-K for gate/up) and batch tiles >= 32 rows; otherwise the [gate; up] layout is kept.
         n_sm = torch.cuda.get_device_properties(device).multi_processor_count
-        self.fuse_silu = bool(fuse_silu and s.inter % 64 == 0 and (2 * s.inter + 127) // 128 >= n_sm and max_batch > 16)
+        tiles, kb = (2 * s.inter + 127) // 128, (s.hidden + 63) // 64
+        gu_splits = max(1, min(8, n_sm // tiles))                 # mirrors pick_splits() in csrc/rr_engine.cu
+        while gu_splits > 1 and kb // gu_splits < 8:
+            gu_splits -= 1
+        self.fuse_silu = bool(fuse_silu and s.inter % 64 == 0 and gu_splits == 1 and max_batch > 16)
         wgu = weights.wgu
         if self.fuse_silu:
             self._wgu_il = []

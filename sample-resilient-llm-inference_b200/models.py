@@ -58,10 +58,16 @@ class ModelSpec:
 SPECS: Dict[str, ModelSpec] = {
     "llama-3-8b": ModelSpec("llama-3-8b", 128256, 4096, 14336, 32, 32, 8, 128, 500000.0, 1e-5),
     "mistral-7b": ModelSpec("mistral-7b", 32000, 4096, 14336, 32, 32, 8, 128, 10000.0, 1e-5),
+    # Phi-3-mini-4k: fused qkv / gate_up are layout only (our layout is fused anyway); head_dim 96, MHA
+    "phi-3-mini": ModelSpec("phi-3-mini", 32064, 3072, 8192, 32, 32, 32, 96, 10000.0, 1e-5),
     # small shapes for parity tests / smoke (same kernels, same code path)
     "tiny": ModelSpec("tiny", 1024, 512, 1024, 2, 4, 2, 128, 500000.0, 1e-5),
     "small": ModelSpec("small", 4096, 1024, 2816, 4, 8, 2, 128, 10000.0, 1e-5),
     "llama-3-8b-2l": ModelSpec("llama-3-8b-2l", 128256, 4096, 14336, 2, 32, 8, 128, 500000.0, 1e-5),
+    "phi-3-mini-2l": ModelSpec("phi-3-mini-2l", 32064, 3072, 8192, 2, 32, 32, 96, 10000.0, 1e-5),
+    "mistral-7b-2l": ModelSpec("mistral-7b-2l", 32000, 4096, 14336, 2, 32, 8, 128, 10000.0, 1e-5),
+    "tiny96": ModelSpec("tiny96", 1024, 384, 1024, 2, 4, 4, 96, 10000.0, 1e-5),
+    "small96": ModelSpec("small96", 4096, 768, 2048, 3, 8, 2, 96, 10000.0, 1e-5),
 }
 
 

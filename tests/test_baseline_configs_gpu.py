@@ -74,11 +74,11 @@ def test_config3_primary_with_injected_failures_falls_back():
     every request is served, failed ones by the fallback group; the primary cools down after allowed_fails."""
     from rr_b200 import Engine, EngineBackend, Router, SPECS, make_weights
     wa = make_weights(SPECS["tiny"], seed=1, sigma=0.05, device="cuda")
-    wb = make_weights(SPECS["small"], seed=2, sigma=0.03, device="cuda")
+    wb = make_weights(SPECS["small96"], seed=2, sigma=0.03, device="cuda")      # Phi-3 family: head_dim 96
     primary = Engine(wa, max_batch=8, ctx_max=256, max_prefill_tokens=512, fail_prob=0.5, fail_seed=42)
     fallback = Engine(wb, max_batch=8, ctx_max=256, max_prefill_tokens=512)
     ml = [{"model_name": "primary", "litellm_params": {"model": "b200/tiny@llama-3-8b", "gpu": 0}},
-          {"model_name": "backup", "litellm_params": {"model": "b200/small@phi-3-mini", "gpu": 1}}]
+          {"model_name": "backup", "litellm_params": {"model": "b200/small96@phi-3-mini", "gpu": 1}}]
     now = [100.0]
     r = Router(model_list=ml, routing_strategy="simple-shuffle", enable_pre_call_checks=True, allowed_fails=2, cooldown_time=15,
                fallbacks=[{"primary": ["backup"]}], backends={0: EngineBackend(primary), 1: EngineBackend(fallback)},

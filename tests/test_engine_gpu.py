@@ -59,19 +59,20 @@ def test_engine_matches_hf_golden_tiny():
         eng.close()
 
 
-@pytest.mark.parametrize("spec_name,max_batch", [("small", 16), ("small", 64), ("llama-3-8b-2l", 64)])
+@pytest.mark.parametrize("spec_name,max_batch", [("small", 16), ("small", 64), ("llama-3-8b-2l", 64), ("tiny96", 8),
+                                                 ("small96", 32), ("phi-3-mini-2l", 64), ("mistral-7b-2l", 64)])
 def test_engine_matches_oracle(spec_name, max_batch):
     from oracle import llama_ref
     from rr_b200.models import SPECS, make_weights
     from rr_b200.engine import Engine
     spec = SPECS[spec_name]
-    w = make_weights(spec, seed=3, sigma=0.03 if spec_name == "small" else 0.02, device="cuda", norm_jitter=0.1)
+    w = make_weights(spec, seed=3, sigma=0.03 if spec.hidden < 2048 else 0.02, device="cuda", norm_jitter=0.1)
     eng = Engine(w, max_batch=max_batch, ctx_max=640, max_prefill_tokens=2048, use_cuda_graph=False)
     try:
         g = torch.Generator().manual_seed(5)
         lens = [3, 64, 129, 300, 512]
         prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in lens]
-        slots = [max_batch - 1, 0, 5, 2, 9]
+        slots = [max_batch - 1, 0, 5, 2, 3]
         first, logits = eng.prefill(prompts, slots, want_logits=True)
         refs = [llama_ref.forward_logits(w, p)[-1] for p in prompts]
         worst = max(_cmp(logits[i], refs[i], f"prefill {spec_name} len={lens[i]}") for i in range(len(lens)))
