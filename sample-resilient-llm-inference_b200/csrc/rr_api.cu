@@ -48,6 +48,7 @@ void rr_trace_set_gemm(unsigned long long*);
 void rr_trace_set_attn_decode(unsigned long long*);
 void rr_trace_set_attn(unsigned long long*);
 void rr_trace_set_elementwise(unsigned long long*);
+void rr_trace_set_chain(unsigned long long*);
 }
 static unsigned long long* g_trace_dev = nullptr;
 static int g_trace_cap = 0;
@@ -63,7 +64,7 @@ RR_API int rr_debug_trace_start(int max_entries) {
     cudaMemcpy(g_trace_dev + 1, &cap, 8, cudaMemcpyHostToDevice);
     g_trace_cap = max_entries;
     rr_trace_set_gemm(g_trace_dev); rr_trace_set_attn_decode(g_trace_dev); rr_trace_set_attn(g_trace_dev);
-    rr_trace_set_elementwise(g_trace_dev);
+    rr_trace_set_elementwise(g_trace_dev); rr_trace_set_chain(g_trace_dev);
     return check_last();
 }
 // Stops tracing and copies up to max_entries (id, start, dep, end) records; returns the number recorded via *n.
@@ -71,7 +72,7 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
     if (!g_trace_dev || !out || !n) return RR_INVALID_ARGUMENT;
     cudaDeviceSynchronize();
     rr_trace_set_gemm(nullptr); rr_trace_set_attn_decode(nullptr); rr_trace_set_attn(nullptr);
-    rr_trace_set_elementwise(nullptr);
+    rr_trace_set_elementwise(nullptr); rr_trace_set_chain(nullptr);
     unsigned long long cnt = 0;
     cudaMemcpy(&cnt, g_trace_dev, 8, cudaMemcpyDeviceToHost);
     int m = (int)(cnt < (unsigned long long)g_trace_cap ? cnt : g_trace_cap);

@@ -104,9 +104,17 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
             if (part.ptr) {
                 const float4 p = part_load4(part, row, c);
                 v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
-                *reinterpret_cast<float4*>(xr + c) = v[i];
             }
             ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+    }
+    // the residual is written back only after every load of this thread has been issued: a store inside the load
+    // loop would fence the following loads (possible aliasing) and turn them into a latency chain
+    if (part.ptr) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (threadIdx.x + i * THREADS) * 4;
+            if (c < hidden) *reinterpret_cast<float4*>(xr + c) = v[i];
         }
     }
     ss = block_sum(ss, red);

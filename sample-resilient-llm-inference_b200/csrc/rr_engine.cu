@@ -103,6 +103,9 @@ struct rr_engine {
     std::vector<DecodeAttnArgs> attn_args;   // per layer (TMA maps of that layer's K / V cache)
     GemmPlan pl_head, pl_head_pf;
     int s_qkv, s_o, s_gu, s_down;
+    bool use_chain = false;           // persistent chain kernel between attention kernels (rr_chain.cu)
+    std::vector<ChainArgs> chain;     // per layer
+    unsigned* chain_counters = nullptr;   // [n_layers][8], zeroed at the start of every step
     bool fuse_silu = false;           // wgu interleaved + one gate/up plane: SiLU*mul lives in the GEMM epilogue
     cudaGraphExec_t graph = nullptr;
     bool warmed = false;
@@ -184,6 +187,22 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
     const rr_model_desc& d = e->d;
     const int B = e->Bm, L = d.n_layers;
     uint64_t nl = 0;
+    if (e->use_chain) {
+        // 3 + 2 L + 1 launches: embed, norm, QKV_0, then per layer attention + one persistent chain kernel
+        cudaMemsetAsync(e->chain_counters, 0, sizeof(unsigned) * 8 * L, s);
+        launch_embed(e->d_tok, (const __nv_bfloat16*)e->embed, e->x, B, d.hidden, e->d_slot, s); ++nl;
+        launch_add_rmsnorm(e->x, part_none(), (const __nv_bfloat16*)e->norm_attn[0], e->xn, B, d.hidden, d.rms_eps, s); ++nl;
+        if (gemm_launch(e->pl_qkv[0], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        for (int l = 0; l < L; ++l) {
+            launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
+            if (launch_decode_chain(e->chain[l], e->bn_dec, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        }
+        launch_argmax(part_f32(e->logits, 1, B, d.vocab), B, d.vocab, e->d_tok, nullptr, e->d_slot, e->d_pos, s); ++nl;
+        if (n_launch) *n_launch = nl;
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) { rr::note_cuda_error(err); return RR_CUDA_ERROR; }
+        return RR_OK;
+    }
     launch_embed(e->d_tok, (const __nv_bfloat16*)e->embed, e->x, B, d.hidden, e->d_slot, s); ++nl;
     launch_add_rmsnorm(e->x, part_none(), (const __nv_bfloat16*)e->norm_attn[0], e->xn, B, d.hidden, d.rms_eps, s); ++nl;
     for (int l = 0; l < L; ++l) {
@@ -578,6 +597,33 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                        B, 1, OUT_TRANSPOSED_F32, e->bn_dec));
     TRY(gemm_plan_init(&e->pl_head_pf, e->lm_head, d.vocab, d.hidden, e->xn_last, B, d.hidden, d.hidden, e->logits,
                        d.vocab, B, 1, OUT_TRANSPOSED_F32, e->bn_dec));
+    e->use_chain = e->fuse_silu && opts->reserved[0] == 0 && e->bn_dec >= 32;
+    if (e->use_chain) {
+        TRY(dalloc(e, &e->chain_counters, (size_t)8 * L));
+        e->chain.resize(L);
+        for (int l = 0; l < L; ++l) {
+            ChainArgs& c = e->chain[l];
+            memset(&c, 0, sizeof(c));
+            TRY(chain_gemm_init(&c.g[0], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->part_o, d.hidden, e->s_o,
+                                OUT_TRANSPOSED_F32, e->bn_dec));
+            TRY(chain_gemm_init(&c.g[1], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, e->act, d.inter, 1,
+                                OUT_TRANSPOSED_SILU, e->bn_dec));
+            TRY(chain_gemm_init(&c.g[2], e->wdown[l], d.hidden, d.inter, e->act, B, e->part_down, d.hidden, e->s_down,
+                                OUT_TRANSPOSED_F32, e->bn_dec));
+            if (l + 1 < L)
+                TRY(chain_gemm_init(&c.g[3], e->wqkv[l + 1], e->nqkv, d.hidden, e->xn, B, e->part_qkv, e->nqkv, e->s_qkv,
+                                    OUT_TRANSPOSED_F32, e->bn_dec));
+            else
+                TRY(chain_gemm_init(&c.g[3], e->lm_head, d.vocab, d.hidden, e->xn, B, e->logits, d.vocab, 1,
+                                    OUT_TRANSPOSED_F32, e->bn_dec));
+            c.n[0].part = e->part_o; c.n[0].n_splits = e->s_o; c.n[0].split_stride = (long long)B * d.hidden;
+            c.n[0].w = (const __nv_bfloat16*)e->norm_mlp[l];
+            c.n[1].part = e->part_down; c.n[1].n_splits = e->s_down; c.n[1].split_stride = (long long)B * d.hidden;
+            c.n[1].w = (const __nv_bfloat16*)((l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm);
+            c.x = e->x; c.xn = e->xn; c.rows = B; c.hidden = d.hidden; c.eps = d.rms_eps;
+            c.counters = e->chain_counters + 8 * l;
+        }
+    }
     TRYC(cudaDeviceSynchronize());
     e->row_req.assign(B, nullptr);
     e->h_slot_mirror.assign(B, -1);

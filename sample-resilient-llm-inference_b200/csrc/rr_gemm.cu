@@ -22,98 +22,17 @@
 //
 // Replaces: the remote bedrock:InvokeModel call (reference iam/policy.json:8,
 // src/demo_cris.py:233-238) — there is no reference kernel; see DESIGN.md §kernels.
-#include "rr_ptx.cuh"
-#include "rr_launch.cuh"
-#include "rr_kernels.h"
+#include "rr_gemm_dev.cuh"
 
 #include <mutex>
 #include <stdio.h>
 
 namespace rr {
 
-constexpr int BLOCK_A = 128;   // UMMA M
-constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_A = 16;    // raster group: 16 A tiles share the streamed B tiles through L2
-
-template <int BN>
-struct GemmCfg {
-    static constexpr int kStageBytesA = BLOCK_A * BLOCK_K * 2;
-    static constexpr int kStageBytesB = BN * BLOCK_K * 2;
-    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr uint32_t kTmemCols =
-        (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int kSiluStageBytes = 2 * 32 * 64 * 4;   // OUT_TRANSPOSED_SILU: up-row exchange, 2 x [32 cols][64 rows] fp32
-};
-template <int MODE>
-__host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }
-template <int BN, int MODE>
-constexpr int gemm_smem_bytes() {
-    return GemmCfg<BN>::kSmemBytes + (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN>::kSiluStageBytes : 0);
-}
-__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.f + __expf(-g)) * u; }
-
-struct WorkItem {
-    int a_tile, b_tile, z, kb0, kb1;
-};
-
-// Deterministic per-CTA sequence of work items; every warp role walks the same sequence.
-struct WorkSched {
-    int tilesA, tilesB, splits, kblocks, n_work, w;
-    long long cur, u_end, U;
-    int streamk;
-
-    __device__ __forceinline__ void init(int rowsA, int rowsB, int K, int splits_, int BN) {
-        tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
-        tilesB = (rowsB + BN - 1) / BN;
-        kblocks = (K + BLOCK_K - 1) / BLOCK_K;
-        streamk = splits_ == 0;
-        splits = splits_;
-        if (streamk) {
-            U = (long long)tilesA * kblocks;
-            cur = (U * blockIdx.x) / gridDim.x;
-            u_end = (U * (blockIdx.x + 1)) / gridDim.x;
-        } else {
-            n_work = tilesA * tilesB * splits;
-            w = blockIdx.x;
-        }
-    }
-    __device__ __forceinline__ bool next(WorkItem& it) {
-        if (streamk) {
-            if (cur >= u_end) return false;
-            const int T = (int)(cur / kblocks);
-            const long long tile_u0 = (long long)T * kblocks;
-            it.a_tile = T;
-            it.b_tile = 0;
-            it.kb0 = (int)(cur - tile_u0);
-            const long long left = u_end - cur;
-            it.kb1 = (kblocks - it.kb0 < left) ? kblocks : it.kb0 + (int)left;
-            // plane = number of CTA range boundaries inside this tile before `cur`
-            const int c_first = (int)(((tile_u0 + 1) * gridDim.x + U - 1) / U) - 1;
-            it.z = (int)blockIdx.x - c_first;
-            cur += it.kb1 - it.kb0;
-            return true;
-        }
-        if (w >= n_work) return false;
-        it.z = w % splits;
-        const int q = w / splits;
-        const int per_group = GROUP_A * tilesB;
-        const int g = q / per_group;
-        const int r = q - g * per_group;
-        const int a0 = g * GROUP_A;
-        const int ga = min(GROUP_A, tilesA - a0);
-        it.a_tile = a0 + r % ga;
-        it.b_tile = r / ga;
-        it.kb0 = (int)(((long long)kblocks * it.z) / splits);
-        it.kb1 = (int)(((long long)kblocks * (it.z + 1)) / splits);
-        w += gridDim.x;
-        return true;
-    }
-};
+#ifndef RR_L2_AHEAD
+#define RR_L2_AHEAD 0
+#endif
+constexpr int kL2Ahead = RR_L2_AHEAD;   // experiment knob (k-blocks of 16 KB per CTA prefetched to L2 before the PDL wait)
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -193,6 +112,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.b_tile * BN, polB);
                 }
+            }
+            if (decode_orient<MODE>() && have && kL2Ahead > 0) {
+                // bounded L2 look-ahead: the next kL2Ahead weight k-blocks of this CTA's panel (beyond the smem ring)
+                const int kb_lim = min(t.kb1, t.kb0 + pre + kL2Ahead);
+                for (int kb = t.kb0 + pre; kb < kb_lim; ++kb) tma_prefetch_l2_2d(&tmA, kb * BLOCK_K, t.a_tile * BLOCK_A);
             }
             griddep_wait();
             trace_dep(tr_slot);

@@ -29,6 +29,31 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn);
 int gemm_launch(const GemmPlan& p, cudaStream_t st);
 
+// ---- persistent decode chain (rr_chain.cu): O GEMM -> norm -> gate/up GEMM -> down GEMM -> norm -> next GEMM
+struct ChainGemm {
+    CUtensorMap tmA, tmB;     // A = weight [rowsA, K] (box 128 rows), B = activations [rows, K] (box bn rows)
+    void* out;                // OUT_TRANSPOSED_F32: fp32 planes [splits][rows][ldo]; OUT_TRANSPOSED_SILU: bf16 [rows][ldo]
+    int rowsA, K, splits, ldo, mode;
+};
+struct ChainNorm {
+    const float* part;        // planes [n_splits][rows][hidden]
+    int n_splits;
+    long long split_stride;
+    const __nv_bfloat16* w;
+};
+struct ChainArgs {
+    ChainGemm g[4];           // O, gate/up, down, next (QKV of the next layer or lm_head)
+    ChainNorm n[2];           // after O (post-attention norm), after down (next layer's input norm / final norm)
+    float* x;                 // residual [rows, hidden] fp32
+    __nv_bfloat16* xn;        // normalised activations [rows, hidden]
+    int rows, hidden;
+    float eps;
+    unsigned* counters;       // [5] grid-barrier counters, zero at launch
+};
+int chain_gemm_init(ChainGemm* g, const void* W, int rowsA, int K, const void* act, int rows, void* out, int ldo,
+                    int splits, int mode, int bn);
+int launch_decode_chain(const ChainArgs& a, int bn, cudaStream_t st);
+
 // ---- elementwise / normalisation (rr_elementwise.cu) -------------------------------------------
 // `part` inputs are the GEMM outputs: either fp32 split-K partials P[z][row][col] (n_splits >= 1,
 // part_is_bf16 = 0, split stride = split_stride elements) or a single bf16 matrix.

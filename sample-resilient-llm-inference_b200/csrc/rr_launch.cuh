@@ -38,6 +38,16 @@ __device__ __forceinline__ int trace_begin(int kid) {
 __device__ __forceinline__ void trace_dep(int slot) {
     if (slot >= 0) rr_trace_ptr[4 + 4 * slot] = rr_gtimer();
 }
+// single-thread marker from inside a kernel (caller guarantees one calling thread in CTA 0)
+__device__ __forceinline__ void trace_mark(int kid) {
+    unsigned long long* p = rr_trace_ptr;
+    if (p == nullptr || (blockIdx.x | blockIdx.y | blockIdx.z) != 0) return;
+    const int slot = (int)atomicAdd(p, 1ull);
+    if (slot >= (int)p[1]) return;
+    const unsigned long long t = rr_gtimer();
+    p[2 + 4 * slot] = (unsigned long long)kid;
+    p[3 + 4 * slot] = t; p[4 + 4 * slot] = t; p[5 + 4 * slot] = t;
+}
 __device__ __forceinline__ void trace_end(int slot) {
     if (slot >= 0) rr_trace_ptr[5 + 4 * slot] = rr_gtimer();
 }
