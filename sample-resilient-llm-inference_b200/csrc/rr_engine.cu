@@ -103,6 +103,7 @@ struct rr_engine {
     std::vector<DecodeAttnArgs> attn_args;   // per layer (TMA maps of that layer's K / V cache)
     GemmPlan pl_head, pl_head_pf;
     int s_qkv, s_o, s_gu, s_down;
+    bool fuse_rope_pf = false;        // prefill: RoPE + KV append live in the QKV GEMM epilogue (head_dim 128)
     bool use_chain = false;           // persistent chain kernel between attention kernels (rr_chain.cu)
     std::vector<ChainArgs> chain;     // per layer
     unsigned* chain_counters = nullptr;   // [n_layers][8], zeroed at the start of every step
@@ -268,8 +269,15 @@ static int get_pf_plans(rr_engine* e, int T, rr_engine::PfPlans** out) {
     P.qkv.resize(L); P.o.resize(L); P.gu.resize(L); P.down.resize(L);
     for (int l = 0; l < L; ++l) {
         int rc = gemm_plan_init(&P.qkv[l], e->pxn, T, d.hidden, e->wqkv[l], e->nqkv, d.hidden, d.hidden, e->pqkv,
-                                e->nqkv, 0, 1, OUT_ROWMAJOR_BF16, 256);
+                                e->nqkv, 0, 1, e->fuse_rope_pf ? OUT_ROWMAJOR_ROPE : OUT_ROWMAJOR_BF16, 256);
         if (rc) return rc;
+        if (e->fuse_rope_pf) {
+            RopeEpi& r = P.qkv[l].rope;
+            r.q_out = e->pq; r.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
+            r.v_cache = e->vcache + (size_t)l * e->kv_layer_stride;
+            r.slot = nullptr; r.pos = nullptr;                     // set per chunk (offsets inside the staging buffer)
+            r.table = e->rope_table; r.n_heads = d.n_heads; r.n_kv_heads = d.n_kv_heads; r.ctx_max = e->o.ctx_max;
+        }
         rc = gemm_plan_init(&P.o[l], e->pattn, T, e->nq, e->wo[l], d.hidden, e->nq, e->nq, e->po, d.hidden, 0, 1,
                             OUT_ROWMAJOR_BF16, 256);
         if (rc) return rc;
@@ -328,13 +336,16 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
     for (int l = 0; l < d.n_layers; ++l) {
         __nv_bfloat16* kc = e->kcache + (size_t)l * e->kv_layer_stride;
         __nv_bfloat16* vc = e->vcache + (size_t)l * e->kv_layer_stride;
+        if (e->fuse_rope_pf) {
+            P->qkv[l].rope.slot = p_slt; P->qkv[l].rope.pos = p_pos;
+        }
         if (gemm_launch(P->qkv[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         RopeArgs ra;
         ra.qkv = part_bf16(e->pqkv, e->nqkv);
         ra.q_out = e->pq; ra.k_cache = kc; ra.v_cache = vc; ra.slot = p_slt; ra.pos = p_pos; ra.rows = T;
         ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max; ra.theta = d.rope_theta;
         ra.table = e->rope_table; ra.head_dim = d.head_dim;
-        launch_rope_kv(ra, s); ++nl;
+        if (!e->fuse_rope_pf) { launch_rope_kv(ra, s); ++nl; }
         PrefillAttnArgs pa;
         pa.q = e->pq; pa.k_cache = kc; pa.v_cache = vc; pa.out = e->pattn; pa.seq_start = p_ss; pa.seq_slot = p_sl;
         pa.n_seqs = n_seqs; pa.max_len = max_len; pa.n_heads = d.n_heads; pa.n_kv_heads = d.n_kv_heads;
@@ -597,6 +608,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                        B, 1, OUT_TRANSPOSED_F32, e->bn_dec));
     TRY(gemm_plan_init(&e->pl_head_pf, e->lm_head, d.vocab, d.hidden, e->xn_last, B, d.hidden, d.hidden, e->logits,
                        d.vocab, B, 1, OUT_TRANSPOSED_F32, e->bn_dec));
+    e->fuse_rope_pf = d.head_dim == 128 && opts->reserved[1] == 0;
     e->use_chain = e->fuse_silu && opts->reserved[0] == 0 && e->bn_dec >= 32;
     if (e->use_chain) {
         TRY(dalloc(e, &e->chain_counters, (size_t)8 * L));

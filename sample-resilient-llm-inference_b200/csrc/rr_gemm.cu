@@ -26,6 +26,7 @@
 
 #include <mutex>
 #include <stdio.h>
+#include <string.h>
 
 namespace rr {
 
@@ -38,7 +39,7 @@ template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   void* __restrict__ out, int rowsA, int rowsB, int K, int splits, int ldo,
-                  int ld_rows) {
+                  int ld_rows, const RopeEpi rope) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
 
@@ -226,6 +227,69 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
+            } else if constexpr (MODE == OUT_ROWMAJOR_ROPE) {
+                // 256 columns = two 128-wide heads of the fused qkv projection; thread = token row.
+                const bool row_ok = a_row < rowsA;
+                const int slot = row_ok ? rope.slot[a_row] : -1;
+                const int pos = row_ok ? rope.pos[a_row] : 0;
+                const bool live = slot >= 0;
+                const float2* tab = rope.table + (size_t)pos * 64;
+#pragma unroll 1
+                for (int hb = 0; hb < BN / 128; ++hb) {
+                    const int H = t.b_tile * (BN / 128) + hb;                  // head index in [q heads | k heads | v heads]
+                    if (H * 128 >= rowsB) break;
+                    const uint32_t tcol = taddr0 + hb * 128;
+                    if (H < rope.n_heads + rope.n_kv_heads) {
+                        __nv_bfloat16* dst = H < rope.n_heads
+                            ? rope.q_out + (size_t)a_row * (rope.n_heads * 128) + H * 128
+                            : rope.k_cache + (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads)) * rope.ctx_max + pos) * 128;
+#pragma unroll 1
+                        for (int c = 0; c < 64; c += 32) {
+                            uint32_t lo[32], hi[32];
+                            tmem_ld_32x32b_x32(tcol + c, lo);
+                            tmem_ld_32x32b_x32(tcol + 64 + c, hi);
+                            tmem_ld_wait();
+                            if (live) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    uint4 plo, phi;
+                                    uint32_t* wl = reinterpret_cast<uint32_t*>(&plo);
+                                    uint32_t* wh = reinterpret_cast<uint32_t*>(&phi);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float4 cs = *reinterpret_cast<const float4*>(tab + c + j + 2 * q);   // 2 pairs
+                                        const float l0 = __uint_as_float(lo[j + 2 * q]), l1 = __uint_as_float(lo[j + 2 * q + 1]);
+                                        const float h0 = __uint_as_float(hi[j + 2 * q]), h1 = __uint_as_float(hi[j + 2 * q + 1]);
+                                        wl[q] = pack_bf16(l0 * cs.x - h0 * cs.y, l1 * cs.z - h1 * cs.w);
+                                        wh[q] = pack_bf16(h0 * cs.x + l0 * cs.y, h1 * cs.z + l1 * cs.w);
+                                    }
+                                    *reinterpret_cast<uint4*>(dst + c + j) = plo;
+                                    *reinterpret_cast<uint4*>(dst + 64 + c + j) = phi;
+                                }
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* dst = rope.v_cache +
+                            (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads - rope.n_kv_heads)) * rope.ctx_max + pos) * 128;
+#pragma unroll 1
+                        for (int c = 0; c < 128; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(tcol + c, v);
+                            tmem_ld_wait();
+                            if (live) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    uint4 pk;
+                                    pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                                    pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                    pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                                    pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                                    *reinterpret_cast<uint4*>(dst + c + j) = pk;
+                                }
+                            }
+                        }
+                    }
+                }
             } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
                 // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
                 // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
@@ -406,7 +470,7 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
         grid = n_work < num_sms() ? n_work : num_sms();
     }
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, MODE>(), st, p.tmA, p.tmB,
-                                p.out, p.rowsA, p.rowsB, p.K, p.streamk ? 0 : p.splits, p.ldo, p.ld_rows);
+                                p.out, p.rowsA, p.rowsB, p.K, p.streamk ? 0 : p.splits, p.ldo, p.ld_rows, p.rope);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
@@ -429,7 +493,9 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     // fused SiLU*mul epilogues: weights row-interleaved in 64-row gate/up blocks, one plane, bf16 act output
     if (mode == OUT_TRANSPOSED_SILU && (splits != 1 || p->streamk || bn < 32 || rowsA % 128 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_SILU && (splits != 1 || bn != 256 || rowsB % 128 != 0 || ldo % 8 != 0)) return RR_ERR_ARG;
-    if (mode < 0 || mode > OUT_ROWMAJOR_SILU) return RR_ERR_ARG;
+    if (mode == OUT_ROWMAJOR_ROPE && (splits != 1 || bn != 256 || rowsB % 128 != 0)) return RR_ERR_ARG;
+    if (mode < 0 || mode > OUT_ROWMAJOR_ROPE) return RR_ERR_ARG;
+    memset(&p->rope, 0, sizeof(p->rope));
     p->rowsA = rowsA; p->rowsB = rowsB; p->K = K; p->out = out; p->ldo = ldo; p->ld_rows = ld_rows;
     p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
     int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
@@ -447,6 +513,7 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
         }                                                                                             \
         if constexpr (BN_ == 256) {                                                                   \
             if (p.mode == OUT_ROWMAJOR_SILU) return launch_one<BN_, OUT_ROWMAJOR_SILU>(p, st);         \
+            if (p.mode == OUT_ROWMAJOR_ROPE) return launch_one<BN_, OUT_ROWMAJOR_ROPE>(p, st);         \
         }                                                                                             \
         return RR_ERR_ARG;
     switch (p.bn) {

@@ -13,12 +13,26 @@ namespace rr {
 #define RR_ERR_ARG RR_INVALID_ARGUMENT
 #define RR_ERR_CUDA RR_CUDA_ERROR
 
-enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1, OUT_TRANSPOSED_SILU = 2, OUT_ROWMAJOR_SILU = 3 };
+enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1, OUT_TRANSPOSED_SILU = 2, OUT_ROWMAJOR_SILU = 3,
+                   OUT_ROWMAJOR_ROPE = 4 };
+
+// OUT_ROWMAJOR_ROPE (prefill QKV projection, head_dim 128): the epilogue rotates q and k (RoPE table), writes q to q_out
+// and appends k / v to the KV cache — no intermediate qkv matrix, no separate rope_kv launch.
+struct RopeEpi {
+    __nv_bfloat16* q_out;     // [T, n_heads*128]
+    __nv_bfloat16* k_cache;   // [slot][kv_head][ctx_max][128]
+    __nv_bfloat16* v_cache;
+    const int32_t* slot;      // per token row
+    const int32_t* pos;
+    const float2* table;      // [ctx_max][64] (cos, sin)
+    int n_heads, n_kv_heads, ctx_max;
+};
 
 struct GemmPlan {
     CUtensorMap tmA, tmB;
     void* out;
     int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas, streamk;
+    RopeEpi rope;             // OUT_ROWMAJOR_ROPE only
 };
 
 int num_sms();
