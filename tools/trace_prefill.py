@@ -22,13 +22,13 @@ a = np.frombuffer(buf, dtype=np.uint64)[: 4 * n.value].reshape(-1, 4).astype(np.
 a = a[np.argsort(a[:, 1])]
 print(f"{n.value} kernels; chunk span {(a[-1, 3] - a[0, 1]) / 1e6:.2f} ms")
 # per layer (after embed, norm0): qkv, rope, attn, o, norm, gu(+silu), down, norm
-names = ["gemm_qkv", "rope", "attn", "gemm_o", "norm_mlp", "gemm_gate_up", "gemm_down", "norm_next"]
+names = ["gemm_qkv(+rope)", "attn", "gemm_o", "norm_mlp", "gemm_gate_up(+silu)", "gemm_down", "norm_next"]
 agg = {}
 for i in range(len(a) - 1):
     kid, s, d, e = a[i]
     seg = (a[i + 1, 2] - d) / 1e3
     if i < 2: nm = ["embed", "norm0"][i]
-    elif i < 2 + 8 * spec.n_layers: nm = names[(i - 2) % 8]
+    elif i < 2 + 7 * spec.n_layers: nm = names[(i - 2) % 7]
     else: nm = "tail(" + NAMES.get(int(kid), str(kid)) + ")"
     x = agg.setdefault(nm, [0, 0.0, 0.0]); x[0] += 1; x[1] += seg; x[2] += (e - d) / 1e3
 tot = sum(v[1] for v in agg.values())
