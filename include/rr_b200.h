@@ -62,10 +62,14 @@ int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n);
 enum {                       /* router_settings.routing_strategy (reference config.yaml:101) */
     RR_STRATEGY_SIMPLE_SHUFFLE = 0,
     RR_STRATEGY_LEAST_BUSY = 1,
-    RR_STRATEGY_ROUND_ROBIN = 2   /* reference src/demo_account_sharding.py:335-343 (req_id % n) */
+    /* client-side distribution strategies of reference src/demo_account_sharding.py:335-343: */
+    RR_STRATEGY_ROUND_ROBIN = 2,  /* req_id % n */
+    RR_STRATEGY_SPLIT = 3,        /* first share of the burst to backend 0, next to backend 1, ... (req_id < N / 2) */
+    RR_STRATEGY_RANDOM = 4        /* random.choice, weights ignored */
 };
 
-enum { RR_EV_ADMIT = 0, RR_EV_DONE = 1, RR_EV_FAIL = 2 };
+/* RR_EV_BURST(target = group, tokens = N) declares the size of the next burst for RR_STRATEGY_SPLIT. */
+enum { RR_EV_ADMIT = 0, RR_EV_DONE = 1, RR_EV_FAIL = 2, RR_EV_BURST = 3 };
 
 typedef struct rr_deployment_desc {
     int32_t group;           /* index of model_name (reference config.yaml:36,44,...) */

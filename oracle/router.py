@@ -34,6 +34,9 @@ pick(group):
   least-busy [UPSTREAM-RECALL least_busy.py]: the first candidate (all of the group, config order)
     with minimum in-flight count; if it is not healthy: random.choice(healthy)
   round-robin (reference src/demo_account_sharding.py:335-343 `req_id % n`): healthy[k % len], k++
+  split (ibid. `req_id < num_requests // 2`, generalised to n backends): request i of a burst of N declared by
+    BURST(group, N) goes to healthy[min(len - 1, i * len // N)]
+  random (ibid. `random.choice`): uniform pick, weights ignored
   debit: req_count += 1, tok_count += n, inflight += 1
 DONE(deployment, completion tokens, now): inflight -= 1; tok_count += tokens (current window)
 FAIL(deployment, now): inflight -= 1; per-minute fail_count += 1; if fail_count > allowed_fails
@@ -48,8 +51,8 @@ from itertools import accumulate as _accumulate
 from typing import Dict, List, Optional, Sequence
 
 RR_OK, RR_RATE_LIMITED, RR_NO_GROUP = 0, 1, 2
-STRATEGY_SIMPLE_SHUFFLE, STRATEGY_LEAST_BUSY, STRATEGY_ROUND_ROBIN = 0, 1, 2
-EV_ADMIT, EV_DONE, EV_FAIL = 0, 1, 2
+STRATEGY_SIMPLE_SHUFFLE, STRATEGY_LEAST_BUSY, STRATEGY_ROUND_ROBIN, STRATEGY_SPLIT, STRATEGY_RANDOM = 0, 1, 2, 3, 4
+EV_ADMIT, EV_DONE, EV_FAIL, EV_BURST = 0, 1, 2, 3
 
 
 @dataclass
@@ -107,6 +110,8 @@ class OracleRouter:
         self.settings = settings
         self.rng = random.Random(seed)
         self.rr_next = [0] * n_groups
+        self.burst_size = [0] * n_groups
+        self.burst_pos = [0] * n_groups
         self.by_group: List[List[int]] = [[] for _ in range(n_groups)]
         for i, d in enumerate(self.deps):
             self.by_group[d.group].append(i)
@@ -161,6 +166,13 @@ class OracleRouter:
             k = self.rr_next[group]
             self.rr_next[group] = k + 1
             return healthy[k % len(healthy)]
+        if st == STRATEGY_SPLIT:
+            n, i = self.burst_size[group], self.burst_pos[group]
+            self.burst_pos[group] = i + 1
+            idx = (i * len(healthy)) // n if n > 0 else 0
+            return healthy[min(idx, len(healthy) - 1)]
+        if st == STRATEGY_RANDOM:
+            return healthy[self.rng._randbelow(len(healthy))]
         raise ValueError(st)
 
     # -- events ------------------------------------------------------------------------------
@@ -214,6 +226,12 @@ class OracleRouter:
                 out.append(self.done(e.target, e.tokens, e.now_ms))
             elif e.type == EV_FAIL:
                 out.append(self.fail(e.target, e.now_ms))
+            elif e.type == EV_BURST:
+                if 0 <= e.target < self.n_groups:
+                    self.burst_size[e.target], self.burst_pos[e.target] = e.tokens, 0
+                    out.append(Decision(RR_OK, -1, e.target, 0))
+                else:
+                    out.append(Decision(RR_NO_GROUP, -1, -1, 0))
             else:
                 out.append(Decision(RR_NO_GROUP, -1, -1, 0))
         return out

@@ -15,7 +15,7 @@ from typing import Any, Dict, List, Optional
 
 import yaml
 
-STRATEGIES = {"simple-shuffle": 0, "least-busy": 1, "round-robin": 2}
+STRATEGIES = {"simple-shuffle": 0, "least-busy": 1, "round-robin": 2, "split": 3, "random": 4}
 _PROVIDER_PREFIXES = ("bedrock/", "b200/", "openai/", "azure/")
 
 

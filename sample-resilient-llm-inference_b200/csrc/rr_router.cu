@@ -48,7 +48,9 @@ struct RouterDev {
     int* inflight;
     long long* cooldown_until;
     long long* total_admitted;
-    int* rr_next;               // [n_groups]
+    int* rr_next;               // [n_groups] round-robin cursor
+    int* burst_size;            // [n_groups] split strategy: size of the declared burst (RR_EV_BURST)
+    int* burst_pos;             // [n_groups] split strategy: requests of the burst seen so far
     uint32_t* mt;               // [624] + index at [624]
 };
 
@@ -218,11 +220,22 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                         const int best = (int)(key & 0xff);
                         if ((mask >> best) & 1u) pick_lane = best;
                         else uniform = true;
-                    } else {   // round robin
+                    } else if (S.strategy == RR_STRATEGY_ROUND_ROBIN) {
                         int k = __ldcg(&S.rr_next[grp]);
                         __syncwarp();
                         if (lane == 0) __stcg(&S.rr_next[grp], k + 1);
                         pick_lane = nth_set_lane(mask, k % nh);
+                    } else if (S.strategy == RR_STRATEGY_SPLIT) {
+                        // contiguous shares of the declared burst: request i of N -> healthy[i * nh / N]
+                        const int n = __ldcg(&S.burst_size[grp]);
+                        const int i = __ldcg(&S.burst_pos[grp]);
+                        __syncwarp();
+                        if (lane == 0) __stcg(&S.burst_pos[grp], i + 1);
+                        int idx = n > 0 ? (int)(((long long)i * nh) / n) : 0;
+                        if (idx > nh - 1) idx = nh - 1;
+                        pick_lane = nth_set_lane(mask, idx);
+                    } else {   // RR_STRATEGY_RANDOM: uniform, weights ignored
+                        uniform = true;
                     }
                     if (uniform) pick_lane = nth_set_lane(mask, (int)rng.randbelow((uint32_t)nh));
                     if (lane == pick_lane) {
@@ -242,6 +255,13 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                     dec.served_group = -1;
                     dec.chain_pos = 0;
                 }
+            }
+        } else if (ev.type == RR_EV_BURST) {
+            const int g = ev.target;
+            if (g >= 0 && g < S.n_groups) {
+                if (lane == 0) { __stcg(&S.burst_size[g], ev.tokens); __stcg(&S.burst_pos[g], 0); }
+                dec.status = RR_OK;
+                dec.served_group = g;
             }
         } else if (ev.type == RR_EV_DONE || ev.type == RR_EV_FAIL) {
             const int d = ev.target;
@@ -357,7 +377,7 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
                             const rr_router_settings* st, uint64_t seed, int device,
                             rr_router** out) {
     if (!deps || !st || !out || n_deps <= 0 || n_groups <= 0 || !fb_offsets) return RR_INVALID_ARGUMENT;
-    if (st->strategy < 0 || st->strategy > RR_STRATEGY_ROUND_ROBIN) return RR_INVALID_ARGUMENT;
+    if (st->strategy < 0 || st->strategy > RR_STRATEGY_RANDOM) return RR_INVALID_ARGUMENT;
     std::vector<int32_t> goff(n_groups + 1, 0), gdeps(n_deps), dgrp(n_deps), rpm(n_deps), tpm(n_deps), wt(n_deps);
     for (int i = 0; i < n_deps; ++i) {
         if (deps[i].group < 0 || deps[i].group >= n_groups) return RR_INVALID_ARGUMENT;
@@ -391,7 +411,8 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
     size_t o_window = take(8 * n_deps), o_failw = take(8 * n_deps), o_cool = take(8 * n_deps),
            o_total = take(8 * n_deps);
     size_t o_req = take(4 * n_deps), o_tok = take(4 * n_deps), o_failc = take(4 * n_deps),
-           o_infl = take(4 * n_deps), o_rr = take(4 * n_groups), o_mt = take(4 * 625);
+           o_infl = take(4 * n_deps), o_rr = take(4 * n_groups), o_bs = take(4 * n_groups), o_bp = take(4 * n_groups),
+           o_mt = take(4 * 625);
     size_t o_goff = take(4 * (n_groups + 1)), o_gdeps = take(4 * n_deps),
            o_fboff = take(4 * (n_groups + 1)), o_fbg = take(4 * (n_fb > 0 ? n_fb : 1)),
            o_dgrp = take(4 * n_deps), o_rpm = take(4 * n_deps), o_tpm = take(4 * n_deps),
@@ -431,6 +452,7 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
     D.fail_count = (int*)(base + o_failc); D.inflight = (int*)(base + o_infl);
     D.cooldown_until = (long long*)(base + o_cool); D.total_admitted = (long long*)(base + o_total);
     D.rr_next = (int*)(base + o_rr); D.mt = (uint32_t*)(base + o_mt);
+    D.burst_size = (int*)(base + o_bs); D.burst_pos = (int*)(base + o_bp);
 
     e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { rr::note_cuda_error(e); cudaFree(r->arena); delete r; return RR_CUDA_ERROR; }

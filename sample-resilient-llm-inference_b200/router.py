@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from .config import RouterConfig, build_config, load_config
 
-EV_ADMIT, EV_DONE, EV_FAIL = 0, 1, 2
+EV_ADMIT, EV_DONE, EV_FAIL, EV_BURST = 0, 1, 2, 3
 
 
 # ---------------------------------------------------------------- errors (OpenAI-SDK names)
@@ -349,7 +349,8 @@ class Router:
         if g < 0:
             raise BadRequestError(f"Invalid model name passed in model={model}")
         now = self.now_ms()
-        dec = self.process([(EV_ADMIT, g, len(p), 0, now) for p in prompts])
+        head = [(EV_BURST, g, len(prompts), 0, now)] if self.cfg.routing_strategy == "split" else []
+        dec = self.process(head + [(EV_ADMIT, g, len(p), 0, now) for p in prompts])[len(head):]
         t0 = time.perf_counter()
         handles: List[Any] = [None] * len(prompts)
         out: List[Any] = [None] * len(prompts)

@@ -146,3 +146,18 @@ def test_invariants(seed, strat, trace):
             assert dep.inflight >= 0
             if dep.rpm >= 0 and dep.window == now // 60000:
                 assert dep.req_count <= dep.rpm
+
+
+def test_split_and_random_strategies():
+    # reference src/demo_account_sharding.py:335-343: split = first half to backend 0, second half to backend 1
+    deps = [O.Deployment(group=0), O.Deployment(group=0)]
+    r = O.OracleRouter(deps, 1, {}, O.Settings(strategy=O.STRATEGY_SPLIT), seed=0)
+    r.process([O.Event(O.EV_BURST, 0, 10, 0, 0)])
+    assert [r.admit(0, 1, 0, i).deployment for i in range(10)] == [0] * 5 + [1] * 5
+    r3 = O.OracleRouter([O.Deployment(group=0) for _ in range(3)], 1, {}, O.Settings(strategy=O.STRATEGY_SPLIT), seed=0)
+    r3.process([O.Event(O.EV_BURST, 0, 7, 0, 0)])
+    assert [r3.admit(0, 1, 0, i).deployment for i in range(9)] == [0, 0, 0, 1, 1, 2, 2, 2, 2]   # overflow stays on the last
+    rr = O.OracleRouter([O.Deployment(group=0, weight=9), O.Deployment(group=0, weight=1)], 1, {},
+                        O.Settings(strategy=O.STRATEGY_RANDOM), seed=5)
+    ref = random.Random(5)
+    assert [rr.admit(0, 1, 0, i).deployment for i in range(50)] == [ref.choice([0, 1]) for _ in range(50)]

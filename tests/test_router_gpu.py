@@ -54,8 +54,10 @@ def _random_trace(rng, n_groups, n_deps, n, admit_only=False):
     now, ev = 0, []
     for _ in range(n):
         now += rng.choice([0, 1, 5, 50, 500, 20_000])
-        t = O.EV_ADMIT if admit_only else rng.choices([0, 1, 2], weights=[6, 3, 1])[0]
-        if t == O.EV_ADMIT:
+        t = O.EV_ADMIT if admit_only else rng.choices([0, 1, 2, 3], weights=[12, 6, 2, 1])[0]
+        if t == O.EV_BURST:
+            ev.append(O.Event(t, rng.randrange(-1, n_groups + 1), rng.randrange(0, 40), 0, now))
+        elif t == O.EV_ADMIT:
             ev.append(O.Event(t, rng.randrange(-1, n_groups + 1), rng.randrange(0, 400),
                               rng.choice([0, 0, 0, 1, 2]), now))
         else:
@@ -76,7 +78,7 @@ def _topology(rng, weighted):
     return deps, n_groups, fbs
 
 
-@pytest.mark.parametrize("strategy", [0, 1, 2])
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("weighted", [False, True])
 @pytest.mark.parametrize("seed", [0, 1, 2**33 + 5])
 def test_kernel_matches_oracle_on_random_traces(strategy, weighted, seed):
