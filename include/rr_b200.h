@@ -152,7 +152,9 @@ enum { RR_OUT_ROWMAJOR_BF16 = 0, RR_OUT_TRANSPOSED_F32 = 1,
        /* fused SiLU(gate)*up epilogues; the weight operand holds gate/up rows interleaved in 64-row blocks
         * [g0..g63, u0..u63, g64..g127, u64..u127, ...] and the output is bf16 act[.., inter]: */
        RR_OUT_TRANSPOSED_SILU = 2,   /* decode: A = interleaved weight [2*inter, K], out[b*ldo + n], splits = 1 */
-       RR_OUT_ROWMAJOR_SILU = 3 };   /* prefill: B = interleaved weight, bn = 256, out[a*ldo + n] */
+       RR_OUT_ROWMAJOR_SILU = 3,     /* prefill: B = interleaved weight, bn = 256, out[a*ldo + n] */
+       RR_OUT_ROWMAJOR_ROPE = 4,     /* engine-internal (prefill QKV epilogue with RoPE + KV scatter) */
+       RR_OUT_ROWMAJOR_RESID = 5 };  /* out = fp32 residual [rowsA, ldo]: out[a*ldo + b] += acc (bn >= 128) */
 
 /* D[a,b] = sum_k A[a,k] B[b,k] on tcgen05 tensor cores (bf16 in, fp32 accumulate).
  * mode RR_OUT_ROWMAJOR_BF16:  out bf16 [rowsA, ldo], out[a*ldo + b]         (splits must be 1)

@@ -138,6 +138,8 @@ void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bflo
     if (rows <= 0 || hidden > 8192) return;
     if (rows <= 256)
         launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps);
+    else if (hidden <= 4096)      // fewer registers -> more rows in flight per SM (HBM-bound at thousands of rows)
+        launch_pdl(add_rmsnorm_kernel<256, 4>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps);
     else
         launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps);
 }

@@ -278,8 +278,8 @@ static int get_pf_plans(rr_engine* e, int T, rr_engine::PfPlans** out) {
             r.slot = nullptr; r.pos = nullptr;                     // set per chunk (offsets inside the staging buffer)
             r.table = e->rope_table; r.n_heads = d.n_heads; r.n_kv_heads = d.n_kv_heads; r.ctx_max = e->o.ctx_max;
         }
-        rc = gemm_plan_init(&P.o[l], e->pattn, T, e->nq, e->wo[l], d.hidden, e->nq, e->nq, e->po, d.hidden, 0, 1,
-                            OUT_ROWMAJOR_BF16, 256);
+        rc = gemm_plan_init(&P.o[l], e->pattn, T, e->nq, e->wo[l], d.hidden, e->nq, e->nq, e->px, d.hidden, 0, 1,
+                            OUT_ROWMAJOR_RESID, 256);                  // residual add in the epilogue
         if (rc) return rc;
         if (e->fuse_silu)
             rc = gemm_plan_init(&P.gu[l], e->pxn, T, d.hidden, e->wgu[l], 2 * d.inter, d.hidden, d.hidden, e->pact,
@@ -288,8 +288,8 @@ static int get_pf_plans(rr_engine* e, int T, rr_engine::PfPlans** out) {
             rc = gemm_plan_init(&P.gu[l], e->pxn, T, d.hidden, e->wgu[l], 2 * d.inter, d.hidden, d.hidden, e->pgu,
                                 2 * d.inter, 0, 1, OUT_ROWMAJOR_BF16, 256);
         if (rc) return rc;
-        rc = gemm_plan_init(&P.down[l], e->pact, T, d.inter, e->wdown[l], d.hidden, d.inter, d.inter, e->po,
-                            d.hidden, 0, 1, OUT_ROWMAJOR_BF16, 256);
+        rc = gemm_plan_init(&P.down[l], e->pact, T, d.inter, e->wdown[l], d.hidden, d.inter, d.inter, e->px,
+                            d.hidden, 0, 1, OUT_ROWMAJOR_RESID, 256);
         if (rc) return rc;
     }
     if (e->pf_plans.size() > 64) e->pf_plans.clear();
@@ -352,13 +352,13 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim); pa.head_dim = d.head_dim;
         launch_prefill_attn(pa, s); ++nl;
         if (gemm_launch(P->o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
+        launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
                            d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(P->gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->fuse_silu) { launch_silu_mul(part_bf16(e->pgu, 2 * d.inter), e->pact, T, d.inter, s); ++nl; }
         if (gemm_launch(P->down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         const void* nw = (l + 1 < d.n_layers) ? e->norm_attn[l + 1] : e->final_norm;
-        launch_add_rmsnorm(e->px, part_bf16(e->po, d.hidden), (const __nv_bfloat16*)nw, e->pxn, T, d.hidden,
+        launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)nw, e->pxn, T, d.hidden,
                            d.rms_eps, s); ++nl;
     }
     launch_pdl(gather_rows_kernel, dim3(n_seqs), dim3(256), 0, s, (const __nv_bfloat16*)e->pxn, (const int32_t*)p_last,

@@ -290,6 +290,30 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
+            } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
+                float* xres = reinterpret_cast<float*>(out);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr0 + c, v);
+                    tmem_ld_wait();
+                    const int b0 = t.b_tile * BN + c;
+                    if (a_row < rowsA) {
+                        float* dst = xres + (size_t)a_row * ldo + b0;
+                        if (b0 + 32 <= rowsB) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 x4 = *reinterpret_cast<const float4*>(dst + j);
+                                x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
+                                x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
+                                *reinterpret_cast<float4*>(dst + j) = x4;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
+                        }
+                    }
+                }
             } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
                 // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
                 // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
@@ -494,7 +518,8 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     if (mode == OUT_TRANSPOSED_SILU && (splits != 1 || p->streamk || bn < 32 || rowsA % 128 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_SILU && (splits != 1 || bn != 256 || rowsB % 128 != 0 || ldo % 8 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_ROPE && (splits != 1 || bn != 256 || rowsB % 128 != 0)) return RR_ERR_ARG;
-    if (mode < 0 || mode > OUT_ROWMAJOR_ROPE) return RR_ERR_ARG;
+    if (mode == OUT_ROWMAJOR_RESID && (splits != 1 || bn < 32 || ldo % 4 != 0)) return RR_ERR_ARG;
+    if (mode < 0 || mode > OUT_ROWMAJOR_RESID) return RR_ERR_ARG;
     memset(&p->rope, 0, sizeof(p->rope));
     p->rowsA = rowsA; p->rowsB = rowsB; p->K = K; p->out = out; p->ldo = ldo; p->ld_rows = ld_rows;
     p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
@@ -510,6 +535,9 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
         if (p.mode == OUT_TRANSPOSED_F32) return launch_one<BN_, OUT_TRANSPOSED_F32>(p, st);           \
         if constexpr (BN_ >= 32) {                                                                    \
             if (p.mode == OUT_TRANSPOSED_SILU) return launch_one<BN_, OUT_TRANSPOSED_SILU>(p, st);     \
+        }                                                                                             \
+        if constexpr (BN_ >= 128) {                                                                   \
+            if (p.mode == OUT_ROWMAJOR_RESID) return launch_one<BN_, OUT_ROWMAJOR_RESID>(p, st);       \
         }                                                                                             \
         if constexpr (BN_ == 256) {                                                                   \
             if (p.mode == OUT_ROWMAJOR_SILU) return launch_one<BN_, OUT_ROWMAJOR_SILU>(p, st);         \

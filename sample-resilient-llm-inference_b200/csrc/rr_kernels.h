@@ -14,7 +14,9 @@ namespace rr {
 #define RR_ERR_CUDA RR_CUDA_ERROR
 
 enum GemmOutMode { OUT_ROWMAJOR_BF16 = 0, OUT_TRANSPOSED_F32 = 1, OUT_TRANSPOSED_SILU = 2, OUT_ROWMAJOR_SILU = 3,
-                   OUT_ROWMAJOR_ROPE = 4 };
+                   OUT_ROWMAJOR_ROPE = 4, OUT_ROWMAJOR_RESID = 5 };
+// OUT_ROWMAJOR_RESID (prefill O / down projections): out is the fp32 residual stream, out[a*ldo + b] += acc —
+// the following norm kernel then only reads x and writes xn (half its bytes).
 
 // OUT_ROWMAJOR_ROPE (prefill QKV projection, head_dim 128): the epilogue rotates q and k (RoPE table), writes q to q_out
 // and appends k / v to the KV cache — no intermediate qkv matrix, no separate rope_kv launch.

@@ -132,3 +132,17 @@ def test_gemm_fused_silu_prefill_orientation(inter, K, T):
     ref = torch.nn.functional.silu(y[:, :inter]) * y[:, inter:]
     assert torch.isfinite(act.float()).all()
     assert torch.allclose(act.float(), ref, atol=2e-2 * ref.abs().max().item(), rtol=2e-2)
+
+
+def test_gemm_residual_epilogue():
+    """OUT_ROWMAJOR_RESID: fp32 residual += A @ B^T (prefill O / down projections)."""
+    from rr_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(77)
+    T, N, K = 1000, 4096, 512
+    A = torch.randn(T, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    x = torch.randn(T, N, device="cuda", generator=g)
+    ref = x + A.float() @ B.float().t()
+    _lib.check(_lib.lib.rr_gemm_bf16(A.data_ptr(), T, K, B.data_ptr(), N, K, K, x.data_ptr(), N, 0, 1, 5, 256, None))
+    torch.cuda.synchronize()
+    assert torch.allclose(x, ref, atol=1e-3 * ref.abs().max().item(), rtol=1e-4)
