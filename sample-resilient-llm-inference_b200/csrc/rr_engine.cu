@@ -42,6 +42,24 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
     for (int c = threadIdx.x; c < hidden / 8; c += blockDim.x) d[c] = s[c];
 }
 
+// Last layer of a prefill chunk: only the last token of every prompt still matters after attention.  Gather those
+// rows (attention output bf16, residual fp32) into the decode working set; the rest of the layer and lm_head then run
+// on n_seqs rows with the weight-streaming (decode-orientation) kernels instead of on all T tokens.
+__global__ void gather_last_kernel(const __nv_bfloat16* __restrict__ attn, const float* __restrict__ x,
+                                   const int32_t* __restrict__ last, __nv_bfloat16* __restrict__ attn_out,
+                                   float* __restrict__ x_out, int nq, int hidden) {
+    griddep_launch();
+    griddep_wait();
+    const int r = blockIdx.x;
+    const size_t src = (size_t)last[r];
+    const uint4* a = reinterpret_cast<const uint4*>(attn + src * nq);
+    uint4* ao = reinterpret_cast<uint4*>(attn_out + (size_t)r * nq);
+    for (int c = threadIdx.x; c < nq / 8; c += blockDim.x) ao[c] = a[c];
+    const float4* xs = reinterpret_cast<const float4*>(x + src * hidden);
+    float4* xo = reinterpret_cast<float4*>(x_out + (size_t)r * hidden);
+    for (int c = threadIdx.x; c < hidden / 4; c += blockDim.x) xo[c] = xs[c];
+}
+
 // After a prefill chunk: row/slot s becomes an active decode row fed with its first token.
 __global__ void activate_rows_kernel(const int32_t* __restrict__ seq_slot, const int32_t* __restrict__ first_tok,
                                      const int32_t* __restrict__ seq_start, int n, int32_t* __restrict__ d_tok,
@@ -351,19 +369,31 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         pa.n_seqs = n_seqs; pa.max_len = max_len; pa.n_heads = d.n_heads; pa.n_kv_heads = d.n_kv_heads;
         pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim); pa.head_dim = d.head_dim;
         launch_prefill_attn(pa, s); ++nl;
+        if (l + 1 == d.n_layers) {
+            // ---- trimmed tail: n_seqs rows through O, MLP, final norm (decode-orientation kernels, decode buffers)
+            const int B = e->Bm;
+            launch_pdl(gather_last_kernel, dim3(n_seqs), dim3(256), 0, s, (const __nv_bfloat16*)e->pattn, (const float*)e->px,
+                       (const int32_t*)p_last, e->attn_out, e->x, e->nq, d.hidden); ++nl;
+            if (gemm_launch(e->pl_o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+            launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l], e->xn,
+                               n_seqs, d.hidden, d.rms_eps, s); ++nl;
+            if (gemm_launch(e->pl_gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+            if (!e->fuse_silu) { launch_silu_mul(part_f32(e->part_gu, e->s_gu, B, 2 * d.inter), e->act, n_seqs, d.inter, s); ++nl; }
+            if (gemm_launch(e->pl_down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+            launch_add_rmsnorm(e->x, part_f32(e->part_down, e->s_down, B, d.hidden), (const __nv_bfloat16*)e->final_norm, e->xn,
+                               n_seqs, d.hidden, d.rms_eps, s); ++nl;
+            break;
+        }
         if (gemm_launch(P->o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
                            d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(P->gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->fuse_silu) { launch_silu_mul(part_bf16(e->pgu, 2 * d.inter), e->pact, T, d.inter, s); ++nl; }
         if (gemm_launch(P->down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        const void* nw = (l + 1 < d.n_layers) ? e->norm_attn[l + 1] : e->final_norm;
-        launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)nw, e->pxn, T, d.hidden,
+        launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)e->norm_attn[l + 1], e->pxn, T, d.hidden,
                            d.rms_eps, s); ++nl;
     }
-    launch_pdl(gather_rows_kernel, dim3(n_seqs), dim3(256), 0, s, (const __nv_bfloat16*)e->pxn, (const int32_t*)p_last,
-               e->xn_last, d.hidden); ++nl;
-    if (gemm_launch(e->pl_head_pf, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+    if (gemm_launch(e->pl_head, s) != RR_OK) return RR_CUDA_ERROR; ++nl;      // B = e->xn (rows 0..n_seqs-1)
     launch_argmax(part_f32(e->logits, 1, e->Bm, d.vocab), n_seqs, d.vocab, e->p_first, nullptr, nullptr, nullptr, s); ++nl;
     launch_pdl(activate_rows_kernel, dim3((n_seqs + 127) / 128), dim3(128), 0, s, (const int32_t*)p_sl,
                (const int32_t*)e->p_first, (const int32_t*)p_ss, n_seqs, e->d_tok, e->d_pos, e->d_slot); ++nl;
