@@ -26,9 +26,220 @@
 
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace rr {
+
+// Epilogue of one work item: TMEM accumulator (this warp's 32 lanes x BN columns at taddr0) -> global memory, in the
+// layout / fusion selected by MODE.  Shared by the 1-CTA kernel, the 2-CTA kernel and (by copy) the chain kernel.
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const WorkItem& t, int quarter, int lane,
+                                              void* __restrict__ out, int rowsA, int rowsB, int ldo, int ld_rows,
+                                              const RopeEpi& rope, float* silu_stage) {
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+    if constexpr (MODE == OUT_TRANSPOSED_SILU) {
+        // gate/up rows are interleaved in blocks of 64: lanes 0..63 of the tile hold gate rows, lanes 64..127 the
+        // matching up rows.  The up warps hand their values over through smem ([col][row] -> conflict-free), the
+        // gate warps write act[b][n] = silu(g) * u as bf16.  rowsA = 2 * inter (interleaved), ldo = inter.
+        float* stage = silu_stage;
+        const bool is_up = quarter >= 2;
+        const int r64 = (quarter & 1) * 32 + lane;
+        const int n = t.a_tile * 64 + r64;
+        __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            float* buf = stage + ((c >> 5) & 1) * (32 * 64);
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr0 + c, v);
+            tmem_ld_wait();
+            if (is_up) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (!is_up && 2 * n < rowsA) {
+                const int b0 = t.b_tile * BN + c;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int b = b0 + j;
+                    if (b < rowsB)
+                        act[(size_t)b * ldo + n] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
+                }
+            }
+        }
+    } else if constexpr (MODE == OUT_ROWMAJOR_ROPE) {
+        // 256 columns = two 128-wide heads of the fused qkv projection; thread = token row.
+        const bool row_ok = a_row < rowsA;
+        const int slot = row_ok ? rope.slot[a_row] : -1;
+        const int pos = row_ok ? rope.pos[a_row] : 0;
+        const bool live = slot >= 0;
+        const float2* tab = rope.table + (size_t)pos * 64;
+#pragma unroll 1
+        for (int hb = 0; hb < BN / 128; ++hb) {
+            const int H = t.b_tile * (BN / 128) + hb;                  // head index in [q heads | k heads | v heads]
+            if (H * 128 >= rowsB) break;
+            const uint32_t tcol = taddr0 + hb * 128;
+            if (H < rope.n_heads + rope.n_kv_heads) {
+                __nv_bfloat16* dst = H < rope.n_heads
+                    ? rope.q_out + (size_t)a_row * (rope.n_heads * 128) + H * 128
+                    : rope.k_cache + (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads)) * rope.ctx_max + pos) * 128;
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 32) {
+                    uint32_t lo[32], hi[32];
+                    tmem_ld_32x32b_x32(tcol + c, lo);
+                    tmem_ld_32x32b_x32(tcol + 64 + c, hi);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 plo, phi;
+                            uint32_t* wl = reinterpret_cast<uint32_t*>(&plo);
+                            uint32_t* wh = reinterpret_cast<uint32_t*>(&phi);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 cs = *reinterpret_cast<const float4*>(tab + c + j + 2 * q);   // 2 pairs
+                                const float l0 = __uint_as_float(lo[j + 2 * q]), l1 = __uint_as_float(lo[j + 2 * q + 1]);
+                                const float h0 = __uint_as_float(hi[j + 2 * q]), h1 = __uint_as_float(hi[j + 2 * q + 1]);
+                                wl[q] = pack_bf16(l0 * cs.x - h0 * cs.y, l1 * cs.z - h1 * cs.w);
+                                wh[q] = pack_bf16(h0 * cs.x + l0 * cs.y, h1 * cs.z + l1 * cs.w);
+                            }
+                            *reinterpret_cast<uint4*>(dst + c + j) = plo;
+                            *reinterpret_cast<uint4*>(dst + 64 + c + j) = phi;
+                        }
+                    }
+                }
+            } else {
+                __nv_bfloat16* dst = rope.v_cache +
+                    (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads - rope.n_kv_heads)) * rope.ctx_max + pos) * 128;
+#pragma unroll 1
+                for (int c = 0; c < 128; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tcol + c, v);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                            pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                            pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                            *reinterpret_cast<uint4*>(dst + c + j) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
+        float* xres = reinterpret_cast<float*>(out);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr0 + c, v);
+            tmem_ld_wait();
+            const int b0 = t.b_tile * BN + c;
+            if (a_row < rowsA) {
+                float* dst = xres + (size_t)a_row * ldo + b0;
+                if (b0 + 32 <= rowsB) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 x4 = *reinterpret_cast<const float4*>(dst + j);
+                        x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
+                        x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
+                        *reinterpret_cast<float4*>(dst + j) = x4;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
+                }
+            }
+        }
+    } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
+        // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
+        // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
+        __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
+        const int n_out = rowsB >> 1;
+#pragma unroll 1
+        for (int hb = 0; hb < BN / 128; ++hb) {
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t vg[32], vu[32];
+                tmem_ld_32x32b_x32(taddr0 + hb * 128 + c, vg);
+                tmem_ld_32x32b_x32(taddr0 + hb * 128 + 64 + c, vu);
+                tmem_ld_wait();
+                const int col = t.b_tile * (BN / 2) + hb * 64 + c;
+                if (a_row < rowsA) {
+                    __nv_bfloat16* dst = act + (size_t)a_row * ldo + col;
+                    if (col + 32 <= n_out) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(silu_mul(__uint_as_float(vg[j + 0]), __uint_as_float(vu[j + 0])),
+                                             silu_mul(__uint_as_float(vg[j + 1]), __uint_as_float(vu[j + 1])));
+                            pk.y = pack_bf16(silu_mul(__uint_as_float(vg[j + 2]), __uint_as_float(vu[j + 2])),
+                                             silu_mul(__uint_as_float(vg[j + 3]), __uint_as_float(vu[j + 3])));
+                            pk.z = pack_bf16(silu_mul(__uint_as_float(vg[j + 4]), __uint_as_float(vu[j + 4])),
+                                             silu_mul(__uint_as_float(vg[j + 5]), __uint_as_float(vu[j + 5])));
+                            pk.w = pack_bf16(silu_mul(__uint_as_float(vg[j + 6]), __uint_as_float(vu[j + 6])),
+                                             silu_mul(__uint_as_float(vg[j + 7]), __uint_as_float(vu[j + 7])));
+                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < n_out)
+                                dst[j] = __float2bfloat16(silu_mul(__uint_as_float(vg[j]), __uint_as_float(vu[j])));
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+        uint32_t v[32];
+        if constexpr (CH == 32) {
+            tmem_ld_32x32b_x32(taddr0 + c, v);
+        } else {
+            uint32_t v16[16];
+            tmem_ld_32x32b_x16(taddr0 + c, v16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v16[j];
+        }
+        tmem_ld_wait();
+        const int b0 = t.b_tile * BN + c;
+        if constexpr (MODE == OUT_ROWMAJOR_BF16) {
+            if (a_row < rowsA) {
+                __nv_bfloat16* dst =
+                    reinterpret_cast<__nv_bfloat16*>(out) + (size_t)a_row * ldo + b0;
+                if (b0 + CH <= rowsB) {
+#pragma unroll
+                    for (int j = 0; j < CH; j += 8) {
+                        uint4 pk;
+                        pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                        pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                        *reinterpret_cast<uint4*>(dst + j) = pk;
+                    }
+                } else {
+                    for (int j = 0; j < CH; ++j)
+                        if (b0 + j < rowsB) dst[j] = __float2bfloat16(__uint_as_float(v[j]));
+                }
+            }
+        } else {
+            float* dst = reinterpret_cast<float*>(out);
+            if (a_row < rowsA) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int b = b0 + j;
+                    if (b < rowsB)
+                        dst[((size_t)t.z * ld_rows + b) * ldo + a_row] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+    }
+}
 
 #ifndef RR_L2_AHEAD
 #define RR_L2_AHEAD 0
@@ -196,208 +407,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tcgen05_fence_after();
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            constexpr int CH = (BN >= 32) ? 32 : 16;
-            if constexpr (MODE == OUT_TRANSPOSED_SILU) {
-                // gate/up rows are interleaved in blocks of 64: lanes 0..63 of the tile hold gate rows, lanes 64..127 the
-                // matching up rows.  The up warps hand their values over through smem ([col][row] -> conflict-free), the
-                // gate warps write act[b][n] = silu(g) * u as bf16.  rowsA = 2 * inter (interleaved), ldo = inter.
-                float* stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
-                const bool is_up = quarter >= 2;
-                const int r64 = (quarter & 1) * 32 + lane;
-                const int n = t.a_tile * 64 + r64;
-                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    float* buf = stage + ((c >> 5) & 1) * (32 * 64);
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr0 + c, v);
-                    tmem_ld_wait();
-                    if (is_up) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
-                    }
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (!is_up && 2 * n < rowsA) {
-                        const int b0 = t.b_tile * BN + c;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int b = b0 + j;
-                            if (b < rowsB)
-                                act[(size_t)b * ldo + n] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
-                        }
-                    }
-                }
-            } else if constexpr (MODE == OUT_ROWMAJOR_ROPE) {
-                // 256 columns = two 128-wide heads of the fused qkv projection; thread = token row.
-                const bool row_ok = a_row < rowsA;
-                const int slot = row_ok ? rope.slot[a_row] : -1;
-                const int pos = row_ok ? rope.pos[a_row] : 0;
-                const bool live = slot >= 0;
-                const float2* tab = rope.table + (size_t)pos * 64;
-#pragma unroll 1
-                for (int hb = 0; hb < BN / 128; ++hb) {
-                    const int H = t.b_tile * (BN / 128) + hb;                  // head index in [q heads | k heads | v heads]
-                    if (H * 128 >= rowsB) break;
-                    const uint32_t tcol = taddr0 + hb * 128;
-                    if (H < rope.n_heads + rope.n_kv_heads) {
-                        __nv_bfloat16* dst = H < rope.n_heads
-                            ? rope.q_out + (size_t)a_row * (rope.n_heads * 128) + H * 128
-                            : rope.k_cache + (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads)) * rope.ctx_max + pos) * 128;
-#pragma unroll 1
-                        for (int c = 0; c < 64; c += 32) {
-                            uint32_t lo[32], hi[32];
-                            tmem_ld_32x32b_x32(tcol + c, lo);
-                            tmem_ld_32x32b_x32(tcol + 64 + c, hi);
-                            tmem_ld_wait();
-                            if (live) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    uint4 plo, phi;
-                                    uint32_t* wl = reinterpret_cast<uint32_t*>(&plo);
-                                    uint32_t* wh = reinterpret_cast<uint32_t*>(&phi);
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const float4 cs = *reinterpret_cast<const float4*>(tab + c + j + 2 * q);   // 2 pairs
-                                        const float l0 = __uint_as_float(lo[j + 2 * q]), l1 = __uint_as_float(lo[j + 2 * q + 1]);
-                                        const float h0 = __uint_as_float(hi[j + 2 * q]), h1 = __uint_as_float(hi[j + 2 * q + 1]);
-                                        wl[q] = pack_bf16(l0 * cs.x - h0 * cs.y, l1 * cs.z - h1 * cs.w);
-                                        wh[q] = pack_bf16(h0 * cs.x + l0 * cs.y, h1 * cs.z + l1 * cs.w);
-                                    }
-                                    *reinterpret_cast<uint4*>(dst + c + j) = plo;
-                                    *reinterpret_cast<uint4*>(dst + 64 + c + j) = phi;
-                                }
-                            }
-                        }
-                    } else {
-                        __nv_bfloat16* dst = rope.v_cache +
-                            (((size_t)slot * rope.n_kv_heads + (H - rope.n_heads - rope.n_kv_heads)) * rope.ctx_max + pos) * 128;
-#pragma unroll 1
-                        for (int c = 0; c < 128; c += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(tcol + c, v);
-                            tmem_ld_wait();
-                            if (live) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    uint4 pk;
-                                    pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                                    pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                    pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                                    pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                                    *reinterpret_cast<uint4*>(dst + c + j) = pk;
-                                }
-                            }
-                        }
-                    }
-                }
-            } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
-                float* xres = reinterpret_cast<float*>(out);
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr0 + c, v);
-                    tmem_ld_wait();
-                    const int b0 = t.b_tile * BN + c;
-                    if (a_row < rowsA) {
-                        float* dst = xres + (size_t)a_row * ldo + b0;
-                        if (b0 + 32 <= rowsB) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 x4 = *reinterpret_cast<const float4*>(dst + j);
-                                x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
-                                x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
-                                *reinterpret_cast<float4*>(dst + j) = x4;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
-                        }
-                    }
-                }
-            } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
-                // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
-                // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
-                __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
-                const int n_out = rowsB >> 1;
-#pragma unroll 1
-                for (int hb = 0; hb < BN / 128; ++hb) {
-#pragma unroll 1
-                    for (int c = 0; c < 64; c += 32) {
-                        uint32_t vg[32], vu[32];
-                        tmem_ld_32x32b_x32(taddr0 + hb * 128 + c, vg);
-                        tmem_ld_32x32b_x32(taddr0 + hb * 128 + 64 + c, vu);
-                        tmem_ld_wait();
-                        const int col = t.b_tile * (BN / 2) + hb * 64 + c;
-                        if (a_row < rowsA) {
-                            __nv_bfloat16* dst = act + (size_t)a_row * ldo + col;
-                            if (col + 32 <= n_out) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    uint4 pk;
-                                    pk.x = pack_bf16(silu_mul(__uint_as_float(vg[j + 0]), __uint_as_float(vu[j + 0])),
-                                                     silu_mul(__uint_as_float(vg[j + 1]), __uint_as_float(vu[j + 1])));
-                                    pk.y = pack_bf16(silu_mul(__uint_as_float(vg[j + 2]), __uint_as_float(vu[j + 2])),
-                                                     silu_mul(__uint_as_float(vg[j + 3]), __uint_as_float(vu[j + 3])));
-                                    pk.z = pack_bf16(silu_mul(__uint_as_float(vg[j + 4]), __uint_as_float(vu[j + 4])),
-                                                     silu_mul(__uint_as_float(vg[j + 5]), __uint_as_float(vu[j + 5])));
-                                    pk.w = pack_bf16(silu_mul(__uint_as_float(vg[j + 6]), __uint_as_float(vu[j + 6])),
-                                                     silu_mul(__uint_as_float(vg[j + 7]), __uint_as_float(vu[j + 7])));
-                                    *reinterpret_cast<uint4*>(dst + j) = pk;
-                                }
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (col + j < n_out)
-                                        dst[j] = __float2bfloat16(silu_mul(__uint_as_float(vg[j]), __uint_as_float(vu[j])));
-                            }
-                        }
-                    }
-                }
-            } else {
-#pragma unroll 1
-            for (int c = 0; c < BN; c += CH) {
-                uint32_t v[32];
-                if constexpr (CH == 32) {
-                    tmem_ld_32x32b_x32(taddr0 + c, v);
-                } else {
-                    uint32_t v16[16];
-                    tmem_ld_32x32b_x16(taddr0 + c, v16);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = v16[j];
-                }
-                tmem_ld_wait();
-                const int b0 = t.b_tile * BN + c;
-                if constexpr (MODE == OUT_ROWMAJOR_BF16) {
-                    if (a_row < rowsA) {
-                        __nv_bfloat16* dst =
-                            reinterpret_cast<__nv_bfloat16*>(out) + (size_t)a_row * ldo + b0;
-                        if (b0 + CH <= rowsB) {
-#pragma unroll
-                            for (int j = 0; j < CH; j += 8) {
-                                uint4 pk;
-                                pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                                pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                                pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                                pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                                *reinterpret_cast<uint4*>(dst + j) = pk;
-                            }
-                        } else {
-                            for (int j = 0; j < CH; ++j)
-                                if (b0 + j < rowsB) dst[j] = __float2bfloat16(__uint_as_float(v[j]));
-                        }
-                    }
-                } else {
-                    float* dst = reinterpret_cast<float*>(out);
-                    if (a_row < rowsA) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            const int b = b0 + j;
-                            if (b < rowsB)
-                                dst[((size_t)t.z * ld_rows + b) * ldo + a_row] = __uint_as_float(v[j]);
-                        }
-                    }
-                }
-            }
-            }
+            epilogue_item<BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, ld_rows, rope,
+                                    reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -410,6 +421,208 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =================================================================================================
+// 2-CTA variant for the prefill orientation (tokens on M): a CTA pair (cluster of 2, same TPC) computes a
+// 256 x 256 tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its own 128 rows of A and only HALF of
+// the 256 B rows per k-block (the tensor core reads the other half from the peer's shared memory), so the smem fill
+// traffic per FLOP halves and the ring holds 6 stages of 32 KB instead of 4 of 48 KB.  The leader CTA (rank 0) issues
+// the MMAs; both CTAs run a TMA producer (2SM TMA form: transaction bytes land on the leader's full barrier) and 4
+// epilogue warps for their own 128 accumulator rows.  tcgen05.commit multicasts "slot free" / "accumulator ready" to
+// both CTAs; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
+constexpr int K2_BN = 256;
+constexpr int K2_STAGE_A = BLOCK_A * BLOCK_K * 2;          // 16 KB: this CTA's 128 rows of A
+constexpr int K2_STAGE_B = 128 * BLOCK_K * 2;              // 16 KB: this CTA's half of the 256 B rows
+constexpr int K2_STAGE = K2_STAGE_A + K2_STAGE_B;
+constexpr int K2_STAGES = 6;
+constexpr int K2_SMEM = K2_STAGES * K2_STAGE + 1024 + 256;
+constexpr int GROUP_PAIRS = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                                uint64_t policy) {
+    // executed by both CTAs; peer bit cleared so the transaction bytes update the leader CTA's barrier
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       void* __restrict__ out, int rowsA, int rowsB, int K, int ldo, const RopeEpi rope) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + K2_STAGES * K2_STAGE_A;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + K2_STAGES * K2_STAGE);
+    uint64_t* empty_bar = full_bar + K2_STAGES;
+    uint64_t* tmem_full = empty_bar + K2_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    griddep_launch();
+    const int tr_slot = trace_begin(TR_GEMM_PF);
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < K2_STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);        // leader's expect_tx arrive; both CTAs' TMA bytes complete on it
+                mbar_init(&empty_bar[s], 1);       // multicast commit
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full[s], 1);       // multicast commit
+                mbar_init(&tmem_empty[s], 8);      // 4 epilogue warps of each CTA (leader's instance is the one waited on)
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                            // peer barriers initialised before any remote arrive / multicast
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int pairsA = (rowsA + 255) / 256;
+    const int tilesB = (rowsB + K2_BN - 1) / K2_BN;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int n_work = pairsA * tilesB;
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    auto decode = [&](int w, int& pa, int& tb) {
+        const int per_group = GROUP_PAIRS * tilesB;
+        const int g = w / per_group, r = w - g * per_group;
+        const int a0 = g * GROUP_PAIRS, ga = min(GROUP_PAIRS, pairsA - a0);
+        pa = a0 + r % ga;
+        tb = r / ga;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            const uint64_t polA = l2_policy_evict_last(), polB = l2_policy_evict_last();
+            griddep_wait();
+            trace_dep(tr_slot);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = cluster_id; w < n_work; w += n_clusters) {
+                int pa, tb;
+                decode(w, pa, tb);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    // The peer needs no arrive of its own: its loads for the next phase are only issued after its
+                    // empty barrier fired, i.e. after the leader consumed the previous phase.
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * K2_STAGE);
+                    tma_load_2d_2sm(smemA + stage * K2_STAGE_A, &tmA, &full_bar[stage], kb * BLOCK_K,
+                                    pa * 256 + (int)rank * 128, polA);
+                    tma_load_2d_2sm(smemB + stage * K2_STAGE_B, &tmB, &full_bar[stage], kb * BLOCK_K,
+                                    tb * K2_BN + (int)rank * 128, polB);
+                    if (++stage == K2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(256, K2_BN);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * K2_BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smemA + stage * K2_STAGE_A));
+                    const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smemB + stage * K2_STAGE_B));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_ss_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (++stage == K2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t empty0_remote = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+        griddep_wait();
+        int it = 0;
+        for (int w = cluster_id; w < n_work; w += n_clusters, ++it) {
+            int pa, tb;
+            decode(w, pa, tb);
+            const int acc = it & 1;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tcgen05_fence_after();
+            WorkItem t;
+            t.a_tile = pa * 2 + (int)rank; t.b_tile = tb; t.z = 0; t.kb0 = 0; t.kb1 = kblocks;
+            const int a_row = t.a_tile * BLOCK_A + row_in_tile;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * K2_BN;
+            epilogue_item<K2_BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, 0, rope, nullptr);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty0_remote + acc * 8);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                            // the peer's tensor core may still read this CTA's shared memory
+    trace_end(tr_slot);
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -498,6 +711,8 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
+static bool decode_orient_rt(int mode) { return mode == OUT_TRANSPOSED_F32 || mode == OUT_TRANSPOSED_SILU; }
+
 // splits >= 1: uniform split-K with `splits` planes.  splits == 0: stream-K (decode orientation, rowsB <= bn);
 // p->splits then holds the number of planes the consumer must sum (gemm_streamk_planes).
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
@@ -525,10 +740,42 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
     int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
     if (rc != RR_OK) return rc;
+    // prefill orientation with 256-wide tiles and at least one full 256-row pair: 2-CTA kernel (B box = 128 rows)
+    p->two_cta = (bn == 256 && !decode_orient_rt(mode) && rowsA >= 256) ? 1 : 0;
+    if (p->two_cta) {
+        rc = make_tmap_bf16_2d(&p->tmB2, B, rowsB, K, ldB, 128);
+        if (rc != RR_OK) return rc;
+    }
     return make_tmap_bf16_2d(&p->tmB, B, rowsB, K, ldB, bn);
 }
 
+template <int MODE>
+static int launch_2cta(const GemmPlan& p, cudaStream_t st) {
+    auto kern = gemm_bf16_tcgen05_2cta<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM) != cudaSuccess) return RR_ERR_CUDA;
+        attr_set = true;
+    }
+    const int pairs = (p.rowsA + 255) / 256, tilesB = (p.rowsB + K2_BN - 1) / K2_BN;
+    int clusters = pairs * tilesB;
+    if (clusters > num_sms() / 2) clusters = num_sms() / 2;
+    cudaError_t le = launch_pdl(kern, dim3(2 * clusters), dim3(GEMM_THREADS), (size_t)K2_SMEM, st, p.tmA, p.tmB2, p.out,
+                                p.rowsA, p.rowsB, p.K, p.ldo, p.rope);
+    return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
+}
+
+int g_use_2cta = getenv("RR_NO_2CTA") ? 0 : 1;
+
 int gemm_launch(const GemmPlan& p, cudaStream_t st) {
+    if (p.two_cta && g_use_2cta) {
+        switch (p.mode) {
+            case OUT_ROWMAJOR_BF16: return launch_2cta<OUT_ROWMAJOR_BF16>(p, st);
+            case OUT_ROWMAJOR_SILU: return launch_2cta<OUT_ROWMAJOR_SILU>(p, st);
+            case OUT_ROWMAJOR_ROPE: return launch_2cta<OUT_ROWMAJOR_ROPE>(p, st);
+            case OUT_ROWMAJOR_RESID: return launch_2cta<OUT_ROWMAJOR_RESID>(p, st);
+        }
+    }
 #define RR_CASE(BN_)                                                                                  \
     case BN_:                                                                                         \
         if (p.mode == OUT_ROWMAJOR_BF16) return launch_one<BN_, OUT_ROWMAJOR_BF16>(p, st);             \

@@ -35,6 +35,8 @@ struct GemmPlan {
     void* out;
     int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas, streamk;
     RopeEpi rope;             // OUT_ROWMAJOR_ROPE only
+    CUtensorMap tmB2;         // 2-CTA kernel: B with a 128-row box (each CTA of the pair stages half of the 256 rows)
+    int two_cta;
 };
 
 int num_sms();
