@@ -1,6 +1,7 @@
 // rr_api.cu — extern "C" surface of librr_b200.so for the kernel-level entry points
 // (include/rr_b200.h §2, §3).  Router: rr_router.cu.  Engine: rr_engine.cu.
 #include "rr_kernels.h"
+#include <vector>
 
 #include <string.h>
 
@@ -47,6 +48,7 @@ namespace rr {
 void rr_trace_set_gemm(unsigned long long*);
 void rr_trace_set_attn_decode(unsigned long long*);
 void rr_trace_set_attn(unsigned long long*);
+void rr_trace_set_attn_tc(unsigned long long*);
 void rr_trace_set_elementwise(unsigned long long*);
 void rr_trace_set_chain(unsigned long long*);
 }
@@ -64,6 +66,7 @@ RR_API int rr_debug_trace_start(int max_entries) {
     cudaMemcpy(g_trace_dev + 1, &cap, 8, cudaMemcpyHostToDevice);
     g_trace_cap = max_entries;
     rr_trace_set_gemm(g_trace_dev); rr_trace_set_attn_decode(g_trace_dev); rr_trace_set_attn(g_trace_dev);
+    rr_trace_set_attn_tc(g_trace_dev);
     rr_trace_set_elementwise(g_trace_dev); rr_trace_set_chain(g_trace_dev);
     return check_last();
 }
@@ -72,6 +75,7 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
     if (!g_trace_dev || !out || !n) return RR_INVALID_ARGUMENT;
     cudaDeviceSynchronize();
     rr_trace_set_gemm(nullptr); rr_trace_set_attn_decode(nullptr); rr_trace_set_attn(nullptr);
+    rr_trace_set_attn_tc(nullptr);
     rr_trace_set_elementwise(nullptr); rr_trace_set_chain(nullptr);
     unsigned long long cnt = 0;
     cudaMemcpy(&cnt, g_trace_dev, 8, cudaMemcpyDeviceToHost);
@@ -215,6 +219,18 @@ RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.seq_start = seq_start;
     a.seq_slot = seq_slot; a.n_seqs = n_seqs; a.max_len = max_len; a.n_heads = n_heads;
     a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale; a.head_dim = 128;
+    if (n_heads / n_kv_heads % 2 == 0 && n_seqs > 0) {
+        // tcgen05 path: the TMA maps need the extents of q and of the caches, which this entry point
+        // does not take -- read them back from the caller's index arrays (standalone op, not the engine path).
+        std::vector<int32_t> h(n_seqs + 1);
+        cudaError_t e = cudaMemcpyAsync(h.data(), seq_slot, sizeof(int32_t) * n_seqs, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h[n_seqs], seq_start + n_seqs, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { note_cuda_error(e); return RR_CUDA_ERROR; }
+        int max_slot = 0;
+        for (int i = 0; i < n_seqs; ++i) max_slot = h[i] > max_slot ? h[i] : max_slot;
+        (void)prefill_attn_make_maps(&a, h[n_seqs], (long long)(max_slot + 1) * n_kv_heads * ctx_max);
+    }
     launch_prefill_attn(a, (cudaStream_t)stream);
     return check_last();
 }

@@ -207,6 +207,7 @@ prefill_attn_kernel(PrefillAttnArgs a) {
 
 void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
     if (a.n_seqs <= 0 || a.max_len <= 0) return;
+    if (prefill_attn_tc_eligible(a)) { launch_prefill_attn_tc(a, st); return; }
     constexpr int smem = 16384 + 2 * 32768;
     static bool attr = false;
     if (!attr) {

@@ -119,6 +119,7 @@ struct rr_engine {
     int kv_splits;
     std::vector<GemmPlan> pl_qkv, pl_o, pl_gu, pl_down;
     std::vector<DecodeAttnArgs> attn_args;   // per layer (TMA maps of that layer's K / V cache)
+    std::vector<PrefillAttnArgs> pf_attn;    // per layer (TMA maps of q and of that layer's K / V cache)
     GemmPlan pl_head, pl_head_pf;
     int s_qkv, s_o, s_gu, s_down;
     bool fuse_rope_pf = false;        // prefill: RoPE + KV append live in the QKV GEMM epilogue (head_dim 128)
@@ -364,7 +365,7 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         ra.n_heads = d.n_heads; ra.n_kv_heads = d.n_kv_heads; ra.ctx_max = e->o.ctx_max; ra.theta = d.rope_theta;
         ra.table = e->rope_table; ra.head_dim = d.head_dim;
         if (!e->fuse_rope_pf) { launch_rope_kv(ra, s); ++nl; }
-        PrefillAttnArgs pa;
+        PrefillAttnArgs pa = e->pf_attn[l];          // per-layer TMA maps made at create
         pa.q = e->pq; pa.k_cache = kc; pa.v_cache = vc; pa.out = e->pattn; pa.seq_start = p_ss; pa.seq_slot = p_sl;
         pa.n_seqs = n_seqs; pa.max_len = max_len; pa.n_heads = d.n_heads; pa.n_kv_heads = d.n_kv_heads;
         pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim); pa.head_dim = d.head_dim;
@@ -611,7 +612,16 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
 
     e->pl_qkv.resize(L); e->pl_o.resize(L); e->pl_gu.resize(L); e->pl_down.resize(L);
     e->attn_args.resize(L);
+    e->pf_attn.resize(L);
     for (int l = 0; l < L; ++l) {
+        {
+            PrefillAttnArgs& pa = e->pf_attn[l];
+            pa.q = e->pq; pa.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
+            pa.v_cache = e->vcache + (size_t)l * e->kv_layer_stride; pa.n_heads = d.n_heads;
+            pa.n_kv_heads = d.n_kv_heads; pa.ctx_max = opts->ctx_max; pa.head_dim = d.head_dim;
+            if (d.n_heads / d.n_kv_heads % 2 == 0 && opts->ctx_max % 64 == 0)
+                TRY(prefill_attn_make_maps(&pa, T, (long long)B * d.n_kv_heads * opts->ctx_max));
+        }
         DecodeAttnArgs& da = e->attn_args[l];
         da.q = e->qbuf; da.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
         da.v_cache = e->vcache + (size_t)l * e->kv_layer_stride; da.out = e->attn_out; da.slot = e->d_slot;

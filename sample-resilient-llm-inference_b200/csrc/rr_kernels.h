@@ -145,7 +145,13 @@ struct PrefillAttnArgs {
     int n_seqs, max_len, n_heads, n_kv_heads, ctx_max;
     float scale;
     int head_dim;             // true head dim: `out` head stride; q / caches padded to 128
+    int has_maps = 0;         // tmQ/tmK/tmV valid (prefill_attn_make_maps): enables the tcgen05 kernel
+    CUtensorMap tmQ, tmK, tmV;
 };
 void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st);
+// tcgen05 path (rr_attn_tc.cu): even GQA group sizes only; launch_prefill_attn dispatches to it.
+int prefill_attn_make_maps(PrefillAttnArgs* a, long long q_rows, long long kv_rows);
+bool prefill_attn_tc_eligible(const PrefillAttnArgs& a);
+int launch_prefill_attn_tc(const PrefillAttnArgs& a, cudaStream_t st);
 
 }  // namespace rr
