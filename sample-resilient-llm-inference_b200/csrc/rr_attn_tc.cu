@@ -5,15 +5,19 @@
 //   warp 0      TMA producer  : Q tiles (128 rows x 128 dims, two query heads that share a kv head) and a
 //                               3-deep ring of K/V tiles (64 keys x 128 dims each) from the KV cache
 //   warp 1      MMA issuer    : S_h = Q_h K^T   (M128 N64  K16 x 8, K-major smem operands)
-//                               O_h = P_h V     (M128 N128 K16 x 4, P K-major from smem, V MN-major as
-//                               it lies in the cache: keys are rows, the head dim is contiguous)
+//                               O_h = P_h V     (M128 N128 K16 x 4, P read from TMEM, V MN-major as it
+//                               lies in the cache: keys are rows, the head dim is contiguous)
 //   warps 2-3   idle (fill warpgroup 0, which drops to 24 registers per thread: setmaxnreg)
 //   warps 4-7   softmax, head 0: thread = one query row (TMEM lane): scale, causal mask, running max,
-//   warps 8-11  softmax, head 1: exp2, row sum, P -> bf16 -> swizzled smem; folds the previous tile's
-//                               O from TMEM into fp32 registers (acc = acc * alpha + O), normalises and
-//                               stores at the end.  240 registers per thread (setmaxnreg.inc).
+//   warps 8-11  softmax, head 1: exp2, row sum, P -> bf16 -> TMEM (tcgen05.st over the S columns it just
+//                               read); folds the previous tile's O from TMEM into fp32 registers
+//                               (acc = acc * alpha + O), normalises and stores at the end.  232 registers
+//                               per thread (setmaxnreg.inc).
 // S is double-buffered in TMEM (2 x 64 columns per head) so QK^T of tile j+1 runs under the softmax of
-// tile j; the two heads alternate on the tensor pipe.  TMEM: 2 x (64 + 64 + 128) = 512 columns.
+// tile j; P(j) overwrites the first 32 columns of S(j) (two bf16 per column) and is the A operand of the
+// PV MMA straight from TMEM, so shared memory only carries Q, K and V.  The tensor pipe executes in issue
+// order, which is what protects the S/P columns: S(j+2) is issued after PV(j).  The two heads alternate
+// on the pipe.  TMEM: 2 x (64 + 64 + 128) = 512 columns.
 //
 // Work item = (sequence, head pair, 128-row query tile), heaviest (last) query tiles first, strided
 // over the CTAs.  Only even GQA group sizes take this path (the pair must share its kv head); the
@@ -34,18 +38,18 @@ constexpr int NH = 2;                   // query heads per CTA
 constexpr int NS = 3;                   // K/V ring depth
 constexpr int TC_THREADS = 128 + 128 * NH;
 constexpr uint32_t Q_BYTES = 32768;     // [2 dim halves][128 rows][128 B]
-constexpr uint32_t P_BYTES = 16384;     // [128 rows][128 B]  (64 keys)
 constexpr uint32_t KV_BYTES = 16384;    // [2 dim halves][64 keys][128 B]
 constexpr uint32_t OFF_Q = 0;
-constexpr uint32_t OFF_P = OFF_Q + NH * Q_BYTES;
-constexpr uint32_t OFF_KV = OFF_P + NH * 2 * P_BYTES;
-constexpr uint32_t OFF_BAR = OFF_KV + NS * 2 * KV_BYTES;
+constexpr uint32_t OFF_KV = OFF_Q + NH * Q_BYTES;
+constexpr uint32_t ST_BYTES = 32768;    // output staging, per head: [128 rows][256 B], 16-byte chunks XOR-swizzled by row
+constexpr uint32_t OFF_ST = OFF_KV + NS * 2 * KV_BYTES;
+constexpr uint32_t OFF_BAR = OFF_ST + NH * ST_BYTES;
 constexpr uint32_t TC_SMEM = OFF_BAR + 256 + 1024;   // + barriers + manual 1024 B alignment slack
 
 struct Bars {
     uint64_t q_full, q_empty;
     uint64_t kv_full[NS], kv_empty[NS];
-    uint64_t s_full[NH][2], s_empty[NH][2];
+    uint64_t s_full[NH][2];
     uint64_t p_full[NH][2];
     uint64_t o_full[NH], o_empty[NH];
     uint32_t tmem;
@@ -75,6 +79,31 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
 }
+// Same with the A operand in TMEM (lane = row, one 32-bit column = two consecutive bf16 along K).
+__device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 constexpr uint32_t IDESC_S = umma_idesc_bf16_f32(TQ, TKV);
 constexpr uint32_t IDESC_PV = umma_idesc_bf16_f32(TQ, 128) | (1u << 16);   // b_major = MN
 
@@ -87,14 +116,26 @@ __device__ __forceinline__ float ex2(float x) {
 struct Work {
     int qt, seq, pair, tok0, len, n_kt;
 };
-__device__ __forceinline__ bool decode_work(const PrefillAttnArgs& a, int w, int n_pairs, int max_qt, Work& k) {
+// Work item w -> (query tile, sequence, head pair).  The sequence bounds (and the slot, for the producer)
+// are loaded one item ahead (WorkFetch) so their latency hides under the current item.
+struct WorkFetch {
+    int tok0 = 0, tok1 = 0, slot = 0;
+};
+__device__ __forceinline__ void fetch_work(const PrefillAttnArgs& a, int w, int n_work, int n_pairs, bool want_slot, WorkFetch& f) {
+    if (w >= n_work) return;
+    const int seq = (w % (a.n_seqs * n_pairs)) / n_pairs;
+    f.tok0 = __ldg(a.seq_start + seq);
+    f.tok1 = __ldg(a.seq_start + seq + 1);
+    if (want_slot) f.slot = __ldg(a.seq_slot + seq);
+}
+__device__ __forceinline__ bool decode_work(const PrefillAttnArgs& a, int w, int n_pairs, int max_qt, const WorkFetch& f, Work& k) {
     const int per_qt = a.n_seqs * n_pairs;
     const int qrev = w / per_qt, rem = w - qrev * per_qt;
     k.qt = max_qt - 1 - qrev;
     k.seq = rem / n_pairs;
     k.pair = rem - k.seq * n_pairs;
-    k.tok0 = a.seq_start[k.seq];
-    k.len = a.seq_start[k.seq + 1] - k.tok0;
+    k.tok0 = f.tok0;
+    k.len = f.tok1 - f.tok0;
     if (k.qt * TQ >= k.len) return false;
     const int causal = 2 * k.qt + 2, avail = (k.len + TKV - 1) / TKV;
     k.n_kt = causal < avail ? causal : avail;
@@ -114,13 +155,13 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(&bars->q_full, 1); mbar_init(&bars->q_empty, 1);
-        for (int s = 0; s < NS; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 4 * NH); }
         for (int h = 0; h < NH; ++h) {
             for (int b = 0; b < 2; ++b) {
-                mbar_init(&bars->s_full[h][b], 1); mbar_init(&bars->s_empty[h][b], 128);
-                mbar_init(&bars->p_full[h][b], 128);
+                mbar_init(&bars->s_full[h][b], 1);
+                mbar_init(&bars->p_full[h][b], 4);          // one arrival per softmax warp
             }
-            mbar_init(&bars->o_full[h], 1); mbar_init(&bars->o_empty[h], 128);
+            mbar_init(&bars->o_full[h], 1); mbar_init(&bars->o_empty[h], 4);
         }
         fence_barrier_init();
     }
@@ -142,13 +183,17 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {          // elect.sync: lets the compiler keep TMA / MMA operands on the uniform datapath
             uint32_t kv_it = 0, q_it = 0;
+            WorkFetch nf;
+            fetch_work(a, blockIdx.x, n_work, n_pairs, true, nf);
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 Work k;
-                if (!decode_work(a, w, n_pairs, max_qt, k)) continue;
+                const WorkFetch f = nf;
+                fetch_work(a, w + gridDim.x, n_work, n_pairs, true, nf);
+                if (!decode_work(a, w, n_pairs, max_qt, f, k)) continue;
                 const int head0 = k.pair * NH, kvh = head0 / G;
-                const int kv_row0 = (a.seq_slot[k.seq] * a.n_kv_heads + kvh) * a.ctx_max;
+                const int kv_row0 = (f.slot * a.n_kv_heads + kvh) * a.ctx_max;
                 mbar_wait(&bars->q_empty, (q_it & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars->q_full, NH * Q_BYTES);
                 for (int h = 0; h < NH; ++h)
@@ -170,37 +215,39 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {          // elect.sync: lets the compiler keep TMA / MMA operands on the uniform datapath
             uint32_t kv_it = 0, q_it = 0, s_it = 0, o_it = 0;
-            const uint32_t q_u = smem_u32(smem + OFF_Q), p_u = smem_u32(smem + OFF_P), kv_u = smem_u32(smem + OFF_KV);
+            const uint32_t q_u = smem_u32(smem + OFF_Q), kv_u = smem_u32(smem + OFF_KV);
             auto pv = [&](uint32_t kvit_t, uint32_t sit_t) {
                 const uint32_t v_u = kv_u + (kvit_t % NS) * 2 * KV_BYTES + KV_BYTES, b = sit_t & 1;
                 for (int h = 0; h < NH; ++h) {
                     mbar_wait(&bars->p_full[h][b], (sit_t >> 1) & 1);
                     mbar_wait(&bars->o_empty[h], (o_it & 1) ^ 1);
                     tcgen05_fence_after();
-                    const uint32_t pa = p_u + (h * 2 + b) * P_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_lo(tmem + h * 256 + 128, desc_lo_kmajor(pa) + ks * 2, desc_lo_mnmajor(v_u) + ks * 128,
-                                IDESC_PV, ks > 0);
+                    for (int ks = 0; ks < 4; ++ks)        // 16 keys = 8 TMEM columns of P per step
+                        umma_ts_lo(tmem + h * 256 + 128, tmem + h * 256 + b * 64 + ks * 8, desc_lo_mnmajor(v_u) + ks * 128,
+                                   IDESC_PV, ks > 0);
                     umma_commit(&bars->o_full[h]);
                 }
-                umma_commit(&bars->kv_empty[kvit_t % NS]);
                 ++o_it;
             };
+            WorkFetch nf;
+            fetch_work(a, blockIdx.x, n_work, n_pairs, false, nf);
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 Work k;
-                if (!decode_work(a, w, n_pairs, max_qt, k)) continue;
+                const WorkFetch f = nf;
+                fetch_work(a, w + gridDim.x, n_work, n_pairs, false, nf);
+                if (!decode_work(a, w, n_pairs, max_qt, f, k)) continue;
                 mbar_wait(&bars->q_full, q_it & 1);
                 ++q_it;
                 for (int j = 0; j < k.n_kt; ++j, ++kv_it, ++s_it) {
                     const uint32_t s = kv_it % NS, b = s_it & 1;
                     mbar_wait(&bars->kv_full[s], (kv_it / NS) & 1);
+                    tcgen05_fence_after();
                     const uint32_t k_u = kv_u + s * 2 * KV_BYTES;
                     for (int h = 0; h < NH; ++h) {
-                        mbar_wait(&bars->s_empty[h][b], ((s_it >> 1) & 1) ^ 1);
-                        tcgen05_fence_after();
+                        // S(j) lands on the columns of S(j-2) / P(j-2): PV(j-2) was issued before, the pipe runs in order
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
                             umma_lo(tmem + h * 256 + b * 64,
@@ -221,10 +268,15 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int h = (warp - 4) >> 2, quarter = warp & 3, row = quarter * 32 + lane;
         const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + h * 256;
         const float sc = a.scale * 1.4426950408889634f;
-        uint32_t s_it = 0, o_it = 0;
+        uint32_t s_it = 0, o_it = 0;      // o_it also numbers the K/V ring slots (one per tile)
+        WorkFetch nf;
+        fetch_work(a, blockIdx.x, n_work, n_pairs, false, nf);
+        uint8_t* stage = smem + OFF_ST + h * ST_BYTES;          // this head's 128 x 256 B output staging tile
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             Work k;
-            if (!decode_work(a, w, n_pairs, max_qt, k)) continue;
+            const WorkFetch f = nf;
+            fetch_work(a, w + gridDim.x, n_work, n_pairs, false, nf);
+            if (!decode_work(a, w, n_pairs, max_qt, f, k)) continue;
             const int head = k.pair * NH + h;
             const int qi = k.qt * TQ + row;                       // query index inside the sequence
             const int last_key = qi < k.len ? qi : k.len - 1;     // causal / ragged bound (inclusive)
@@ -237,15 +289,22 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 mbar_wait(&bars->o_full[h], o_it & 1);
                 tcgen05_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_base + 128 + c * 32, v);
+                for (int c = 0; c < 4; c += 2) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(t_base + 128 + c * 32, v0);
+                    tmem_ld_32x32b_x32(t_base + 128 + c * 32 + 32, v1);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(v0[i]));
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[c * 32 + 32 + i] = fmaf(acc[c * 32 + 32 + i], alpha_prev, __uint_as_float(v1[i]));
                 }
                 tcgen05_fence_before();
-                mbar_arrive(&bars->o_empty[h]);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->o_empty[h]);
+                    mbar_arrive(&bars->kv_empty[o_it % NS]);      // PV of this tile is complete: K/V slot is free for this head
+                }
                 ++o_it;
             };
 
@@ -257,76 +316,79 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 const int key0 = j * TKV;
                 const bool need_mask = (key0 + TKV - 1 > k.qt * TQ) || (key0 + TKV > k.len);
                 const int lim = last_key - key0;                  // keep columns c <= lim
-                // ---- pass 1: row max
-                float mx = -INFINITY;
+                uint32_t v0[32], v1[32];                          // the whole S row of this query
+                tmem_ld_32x32b_x32(tS, v0);
+                tmem_ld_32x32b_x32(tS + 32, v1);
+                tmem_ld_wait();
+                if (need_mask) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tS + half * 32, v);
-                    tmem_ld_wait();
-                    if (need_mask) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (half * 32 + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        if (i > lim) v0[i] = 0xff800000u;         // -inf
+                        if (32 + i > lim) v1[i] = 0xff800000u;
                     }
                 }
-                const float m_new = fmaxf(m, mx * sc);
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
+                }
+                const float m_new = fmaxf(m, fmaxf(mx0, mx1) * sc);
                 const float ms = m_new == -INFINITY ? 0.f : m_new;
                 const float alpha = ex2(m - ms);
                 m = m_new;
-                // ---- pass 2: P = exp2(S * sc - m), row sum, bf16 -> swizzled smem (K-major A operand)
-                float ps = 0.f;
-                uint8_t* prow = smem + OFF_P + (h * 2 + b) * P_BYTES + row * 128;
+                // ---- P = exp2(S * sc - m) -> bf16 pairs -> TMEM columns [0, 32) of this S buffer
+                float ps0 = 0.f, ps1 = 0.f;
+                uint32_t pk[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tS + half * 32, v);
-                    tmem_ld_wait();
-                    if (half == 1) {                              // S(j) fully read: release the buffer
-                        tcgen05_fence_before();
-                        mbar_arrive(&bars->s_empty[h][b]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float e[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            e[i] = ex2(fmaf(__uint_as_float(v[u * 8 + i]), sc, -ms));
-                            if (need_mask && half * 32 + u * 8 + i > lim) e[i] = 0.f;
-                            ps += e[i];
-                        }
-                        uint4 pk;
-                        pk.x = pack_bf16(e[0], e[1]);
-                        pk.y = pack_bf16(e[2], e[3]);
-                        pk.z = pack_bf16(e[4], e[5]);
-                        pk.w = pack_bf16(e[6], e[7]);
-                        *reinterpret_cast<uint4*>(prow + (((half * 4 + u) ^ (row & 7)) << 4)) = pk;
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    const float e0 = ex2(fmaf(__uint_as_float(v0[2 * i]), sc, -ms));
+                    const float e1 = ex2(fmaf(__uint_as_float(v0[2 * i + 1]), sc, -ms));
+                    const float e2 = ex2(fmaf(__uint_as_float(v1[2 * i]), sc, -ms));
+                    const float e3 = ex2(fmaf(__uint_as_float(v1[2 * i + 1]), sc, -ms));
+                    ps0 += e0 + e1;
+                    ps1 += e2 + e3;
+                    pk[i] = pack_bf16(e0, e1);
+                    pk[16 + i] = pack_bf16(e2, e3);
                 }
-                l = l * alpha + ps;
-                fence_proxy_async();
-                mbar_arrive(&bars->p_full[h][b]);
+                tmem_st_32x32b_x32(tS, pk);
+                l = l * alpha + (ps0 + ps1);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->p_full[h][b]);
                 if (j > 0) fold();
                 alpha_prev = alpha;
             }
             fold();
-            // ---- normalise + store (row = one token, 128 contiguous dims of this head)
-            if (qi < k.len) {
+            // ---- normalise; stage the warp's 32 rows in smem, then store them row-contiguously (2 rows of
+            //      256 B per warp instruction instead of 32 scattered 16 B pieces)
+            {
                 const float inv = l > 0.f ? 1.f / l : 0.f;
-                __nv_bfloat16* dst = a.out + (size_t)(k.tok0 + qi) * a.n_heads * a.head_dim + (size_t)head * a.head_dim;
+                uint8_t* srow = stage + row * 256;
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                    if (u * 8 >= a.head_dim) break;               // dims beyond the true head dim are padding
                     uint4 pk;
                     pk.x = pack_bf16(acc[u * 8 + 0] * inv, acc[u * 8 + 1] * inv);
                     pk.y = pack_bf16(acc[u * 8 + 2] * inv, acc[u * 8 + 3] * inv);
                     pk.z = pack_bf16(acc[u * 8 + 4] * inv, acc[u * 8 + 5] * inv);
                     pk.w = pack_bf16(acc[u * 8 + 6] * inv, acc[u * 8 + 7] * inv);
-                    *reinterpret_cast<uint4*>(dst + u * 8) = pk;
+                    *reinterpret_cast<uint4*>(srow + ((u ^ (row & 7)) << 4)) = pk;
                 }
+                __syncwarp();
+                const int c = lane & 15;                          // 16-byte chunk = 8 dims
+                const size_t row_pitch = (size_t)a.n_heads * a.head_dim;
+                __nv_bfloat16* obase = a.out + (size_t)k.tok0 * row_pitch + (size_t)head * a.head_dim + c * 8;
+                if (c * 8 < a.head_dim) {                         // dims beyond the true head dim are padding
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = quarter * 32 + 2 * i + (lane >> 4);
+                        const int qr = k.qt * TQ + rr;
+                        const uint4 pk = *reinterpret_cast<const uint4*>(stage + rr * 256 + ((c ^ (rr & 7)) << 4));
+                        if (qr < k.len) *reinterpret_cast<uint4*>(obase + (size_t)qr * row_pitch) = pk;
+                    }
+                }
+                __syncwarp();
             }
         }
     }
