@@ -10,7 +10,7 @@ import pytest
 
 from oracle import router as O
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("rpm_window")]
 
 
 def _oracle_from_cfg(cfg, seed):

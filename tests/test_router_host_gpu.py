@@ -9,19 +9,9 @@ import time
 
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("rpm_window")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CFG = os.path.join(ROOT, "config", "config.yaml")
-
-
-@pytest.fixture(autouse=True)
-def _stay_inside_one_rpm_window():
-    """The tests below that run on the wall clock count admissions against per-minute rpm buckets; started in the
-    last seconds of a minute they would straddle a window refill.  Wait the boundary out instead."""
-    left = 60.0 - time.time() % 60.0
-    if left < 8.0:
-        time.sleep(left + 0.05)
-    yield
 
 
 def _stub_router(clock=None, **kw):
