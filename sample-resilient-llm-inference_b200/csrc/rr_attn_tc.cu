@@ -7,17 +7,23 @@
 //   warp 1      MMA issuer    : S_h = Q_h K^T   (M128 N64  K16 x 8, K-major smem operands)
 //                               O_h = P_h V     (M128 N128 K16 x 4, P read from TMEM, V MN-major as it
 //                               lies in the cache: keys are rows, the head dim is contiguous)
-//   warps 2-3   idle (fill warpgroup 0, which drops to 24 registers per thread: setmaxnreg)
+//   warps 2-3   idle
 //   warps 4-7   softmax, head 0: thread = one query row (TMEM lane): scale, causal mask, running max,
 //   warps 8-11  softmax, head 1: exp2, row sum, P -> bf16 -> TMEM (tcgen05.st over the S columns it just
-//                               read); folds the previous tile's O from TMEM into fp32 registers
-//                               (acc = acc * alpha + O), normalises and stores at the end.  232 registers
-//                               per thread (setmaxnreg.inc).
+//                               read); at the end of the item reads O from TMEM, normalises, stages the
+//                               rows in smem and stores them row-contiguously.
 // S is double-buffered in TMEM (2 x 64 columns per head) so QK^T of tile j+1 runs under the softmax of
 // tile j; P(j) overwrites the first 32 columns of S(j) (two bf16 per column) and is the A operand of the
 // PV MMA straight from TMEM, so shared memory only carries Q, K and V.  The tensor pipe executes in issue
 // order, which is what protects the S/P columns: S(j+2) is issued after PV(j).  The two heads alternate
 // on the pipe.  TMEM: 2 x (64 + 64 + 128) = 512 columns.
+//
+// O accumulates in TMEM across the key tiles of an item (PV with the accumulate flag).  The exponentials
+// of a row are taken relative to a reference maximum that is only raised when the running maximum has
+// moved by more than 2^8 (warp-uniform vote); raising it rescales the warp's 32 rows of O in TMEM
+// (ld, multiply, st) after the previous PV has completed.  exp2(s - ref) <= 256 keeps P exact to bf16
+// precision and the final O / l is independent of the reference, so the rescale is rare instead of once
+// per tile.
 //
 // Work item = (sequence, head pair, 128-row query tile), heaviest (last) query tiles first, strided
 // over the CTAs.  Only even GQA group sizes take this path (the pair must share its kv head); the
@@ -51,7 +57,7 @@ struct Bars {
     uint64_t kv_full[NS], kv_empty[NS];
     uint64_t s_full[NH][2];
     uint64_t p_full[NH][2];
-    uint64_t o_full[NH], o_empty[NH];
+    uint64_t o_full[NH][2], o_free[NH];   // o_full alternates by tile parity, see the softmax warps
     uint32_t tmem;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
@@ -155,13 +161,13 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(&bars->q_full, 1); mbar_init(&bars->q_empty, 1);
-        for (int s = 0; s < NS; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 4 * NH); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
         for (int h = 0; h < NH; ++h) {
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&bars->s_full[h][b], 1);
                 mbar_init(&bars->p_full[h][b], 4);          // one arrival per softmax warp
             }
-            mbar_init(&bars->o_full[h], 1); mbar_init(&bars->o_empty[h], 4);
+            mbar_init(&bars->o_full[h][0], 1); mbar_init(&bars->o_full[h][1], 1); mbar_init(&bars->o_free[h], 4);
         }
         fence_barrier_init();
     }
@@ -179,8 +185,6 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     griddep_wait();
     trace_dep(tr_slot);
 
-    if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {          // elect.sync: lets the compiler keep TMA / MMA operands on the uniform datapath
@@ -215,22 +219,24 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (elect_one()) {          // elect.sync: lets the compiler keep TMA / MMA operands on the uniform datapath
-            uint32_t kv_it = 0, q_it = 0, s_it = 0, o_it = 0;
+        if (elect_one()) {
+            uint32_t kv_it = 0, q_it = 0, s_it = 0, item_it = 0;
             const uint32_t q_u = smem_u32(smem + OFF_Q), kv_u = smem_u32(smem + OFF_KV);
-            auto pv = [&](uint32_t kvit_t, uint32_t sit_t) {
+            // O_h (+)= P_h(t) V(t).  `first`: tile 0 of the item overwrites O, which the softmax warps must
+            // have finished reading for the previous item (o_free).
+            auto pv = [&](uint32_t kvit_t, uint32_t sit_t, bool first) {
                 const uint32_t v_u = kv_u + (kvit_t % NS) * 2 * KV_BYTES + KV_BYTES, b = sit_t & 1;
                 for (int h = 0; h < NH; ++h) {
                     mbar_wait(&bars->p_full[h][b], (sit_t >> 1) & 1);
-                    mbar_wait(&bars->o_empty[h], (o_it & 1) ^ 1);
+                    if (first) mbar_wait(&bars->o_free[h], (item_it & 1) ^ 1);
                     tcgen05_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)        // 16 keys = 8 TMEM columns of P per step
                         umma_ts_lo(tmem + h * 256 + 128, tmem + h * 256 + b * 64 + ks * 8, desc_lo_mnmajor(v_u) + ks * 128,
-                                   IDESC_PV, ks > 0);
-                    umma_commit(&bars->o_full[h]);
+                                   IDESC_PV, (ks > 0 || !first) ? 1u : 0u);
+                    umma_commit(&bars->o_full[h][b]);
                 }
-                ++o_it;
+                umma_commit(&bars->kv_empty[kvit_t % NS]);
             };
             WorkFetch nf;
             fetch_work(a, blockIdx.x, n_work, n_pairs, false, nf);
@@ -256,19 +262,18 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         umma_commit(&bars->s_full[h][b]);
                     }
                     if (j == k.n_kt - 1) umma_commit(&bars->q_empty);
-                    if (j > 0) pv(kv_it - 1, s_it - 1);
+                    if (j > 0) pv(kv_it - 1, s_it - 1, j == 1);
                 }
-                pv(kv_it - 1, s_it - 1);
+                pv(kv_it - 1, s_it - 1, k.n_kt == 1);
+                ++item_it;
             }
         }
-    }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    } else if (warp >= 4) {
         // ------------------------------------------------------------------ softmax + output
         const int h = (warp - 4) >> 2, quarter = warp & 3, row = quarter * 32 + lane;
         const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + h * 256;
         const float sc = a.scale * 1.4426950408889634f;
-        uint32_t s_it = 0, o_it = 0;      // o_it also numbers the K/V ring slots (one per tile)
+        uint32_t s_it = 0;                 // global tile counter: S/P buffer, and the o_full phase of that tile's PV
         WorkFetch nf;
         fetch_work(a, blockIdx.x, n_work, n_pairs, false, nf);
         uint8_t* stage = smem + OFF_ST + h * ST_BYTES;          // this head's 128 x 256 B output staging tile
@@ -280,33 +285,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const int head = k.pair * NH + h;
             const int qi = k.qt * TQ + row;                       // query index inside the sequence
             const int last_key = qi < k.len ? qi : k.len - 1;     // causal / ragged bound (inclusive)
-            float acc[128];
-#pragma unroll
-            for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-            float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-
-            auto fold = [&]() {      // acc = acc * alpha(prev tile) + O(prev tile)
-                mbar_wait(&bars->o_full[h], o_it & 1);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int c = 0; c < 4; c += 2) {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld_32x32b_x32(t_base + 128 + c * 32, v0);
-                    tmem_ld_32x32b_x32(t_base + 128 + c * 32 + 32, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(v0[i]));
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[c * 32 + 32 + i] = fmaf(acc[c * 32 + 32 + i], alpha_prev, __uint_as_float(v1[i]));
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bars->o_empty[h]);
-                    mbar_arrive(&bars->kv_empty[o_it % NS]);      // PV of this tile is complete: K/V slot is free for this head
-                }
-                ++o_it;
-            };
+            float m_ref = -INFINITY, l = 0.f;                     // reference maximum (log2 domain), row sum
 
             for (int j = 0; j < k.n_kt; ++j, ++s_it) {
                 const uint32_t b = s_it & 1;
@@ -333,11 +312,33 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
                     mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
                 }
-                const float m_new = fmaxf(m, fmaxf(mx0, mx1) * sc);
-                const float ms = m_new == -INFINITY ? 0.f : m_new;
-                const float alpha = ex2(m - ms);
-                m = m_new;
-                // ---- P = exp2(S * sc - m) -> bf16 pairs -> TMEM columns [0, 32) of this S buffer
+                const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1) * sc);
+                if (j == 0) {
+                    m_ref = m_new;
+                } else if (__any_sync(0xffffffffu, m_new > m_ref + 8.f)) {
+                    // raise the reference: O and l of this warp's rows move to the new scale.  PV(j-1) must be
+                    // complete, and PV(j) cannot start before this warp arrives on p_full(j) below.  o_full is
+                    // not waited on every tile, so it alternates between two barriers: the previous phase of the
+                    // one PV(t) commits to belongs to PV(t-2), which is complete once S(t+1) or later is (in-order
+                    // pipe) -- the parity wait can never be a phase behind.
+                    const float alpha = ex2(m_ref - (m_new == -INFINITY ? 0.f : m_new));
+                    m_ref = m_new;
+                    l *= alpha;
+                    mbar_wait(&bars->o_full[h][(s_it - 1) & 1], ((s_it - 1) >> 1) & 1);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_32x32b_x32(t_base + 128 + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32b_x32(t_base + 128 + c * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+                const float ms = m_ref == -INFINITY ? 0.f : m_ref;
+                // ---- P = exp2(S * sc - ref) -> bf16 pairs -> TMEM columns [0, 32) of this S buffer
                 float ps0 = 0.f, ps1 = 0.f;
                 uint32_t pk[32];
 #pragma unroll
@@ -352,30 +353,37 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     pk[16 + i] = pack_bf16(e2, e3);
                 }
                 tmem_st_32x32b_x32(tS, pk);
-                l = l * alpha + (ps0 + ps1);
+                l += ps0 + ps1;
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->p_full[h][b]);
-                if (j > 0) fold();
-                alpha_prev = alpha;
             }
-            fold();
-            // ---- normalise; stage the warp's 32 rows in smem, then store them row-contiguously (2 rows of
-            //      256 B per warp instruction instead of 32 scattered 16 B pieces)
+            // ---- O complete after the last PV (phase s_it - 1): normalise; stage the warp's 32 rows in smem, then
+            //      store them row-contiguously (2 rows of 256 B per warp instruction instead of 32 scattered pieces)
+            mbar_wait(&bars->o_full[h][(s_it - 1) & 1], ((s_it - 1) >> 1) & 1);
+            tcgen05_fence_after();
             {
                 const float inv = l > 0.f ? 1.f / l : 0.f;
                 uint8_t* srow = stage + row * 256;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    uint4 pk;
-                    pk.x = pack_bf16(acc[u * 8 + 0] * inv, acc[u * 8 + 1] * inv);
-                    pk.y = pack_bf16(acc[u * 8 + 2] * inv, acc[u * 8 + 3] * inv);
-                    pk.z = pack_bf16(acc[u * 8 + 4] * inv, acc[u * 8 + 5] * inv);
-                    pk.w = pack_bf16(acc[u * 8 + 6] * inv, acc[u * 8 + 7] * inv);
-                    *reinterpret_cast<uint4*>(srow + ((u ^ (row & 7)) << 4)) = pk;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32b_x32(t_base + 128 + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 pk;
+                        pk.x = pack_bf16(__uint_as_float(o[u * 8 + 0]) * inv, __uint_as_float(o[u * 8 + 1]) * inv);
+                        pk.y = pack_bf16(__uint_as_float(o[u * 8 + 2]) * inv, __uint_as_float(o[u * 8 + 3]) * inv);
+                        pk.z = pack_bf16(__uint_as_float(o[u * 8 + 4]) * inv, __uint_as_float(o[u * 8 + 5]) * inv);
+                        pk.w = pack_bf16(__uint_as_float(o[u * 8 + 6]) * inv, __uint_as_float(o[u * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(srow + (((c * 4 + u) ^ (row & 7)) << 4)) = pk;
+                    }
                 }
+                tcgen05_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->o_free[h]);     // O may be overwritten by the next item's first PV
                 const int c = lane & 15;                          // 16-byte chunk = 8 dims
                 const size_t row_pitch = (size_t)a.n_heads * a.head_dim;
                 __nv_bfloat16* obase = a.out + (size_t)k.tok0 * row_pitch + (size_t)head * a.head_dim + c * 8;
