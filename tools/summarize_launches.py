@@ -1,11 +1,12 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list of tools/profile_step.py:
-prefill chunk = launches before the last 2*291 of ours, decode step = the last 291."""
+prefill chunk = launches before the last 2*n_dec of ours, decode step = the last n_dec (228: 7 per layer + 4)."""
 import csv, collections, re, sys
-path = sys.argv[1]; n_dec = int(sys.argv[2]) if len(sys.argv) > 2 else 291
+path = sys.argv[1]; n_dec = int(sys.argv[2]) if len(sys.argv) > 2 else 228
 lines = [l for l in open(path) if not l.startswith('==')]
 rows = [(int(r['ID']), r['Kernel Name'], float(r['Metric Value']), r['Grid Size']) for r in csv.DictReader(lines)
         if r.get('Metric Name') == 'gpu__time_duration.sum']
 def short(n):
+    n = n.replace('<unnamed>::', '').replace('unnamed>::', '')
     m = re.match(r'(void )?(rr::)?(\w+)(<[^>]*>)?', n); return (m.group(3) + (m.group(4) or '')) if m else n[:40]
 print(f"{path}: {len(rows)} launches (per-launch times are cold-cache + serialised: compare SHARES)")
 for name, part in (('PREFILL chunk (16 x 512 tokens)', rows[:len(rows) - 2 * n_dec]), ('DECODE step (64 rows, ctx 577)', rows[-n_dec:])):
