@@ -209,11 +209,8 @@ void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
     if (a.n_seqs <= 0 || a.max_len <= 0) return;
     if (prefill_attn_tc_eligible(a)) { launch_prefill_attn_tc(a, st); return; }
     constexpr int smem = 16384 + 2 * 32768;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(prefill_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr{0};
+    if (ensure_dyn_smem(prefill_attn_kernel, smem, attr) != cudaSuccess) return;
     dim3 grid((a.max_len + PF_Q - 1) / PF_Q, a.n_heads, a.n_seqs);
     launch_pdl(prefill_attn_kernel, grid, dim3(PF_THREADS), (size_t)smem, st, a);
 }

@@ -383,11 +383,8 @@ int decode_attn_make_maps(DecodeAttnArgs* a, int n_slots) {
 
 template <int G>
 static void launch_dec(const DecodeAttnArgs& a, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(decode_attn_mma_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr{0};
+    if (ensure_dyn_smem(decode_attn_mma_kernel<G>, DEC_SMEM, attr) != cudaSuccess) return;
     dim3 grid(a.n_kv_heads, a.rows, a.kv_splits);
     launch_pdl(decode_attn_mma_kernel<G>, grid, dim3(DEC_THREADS), (size_t)DEC_SMEM, st, a);
     if (a.kv_splits > 1)

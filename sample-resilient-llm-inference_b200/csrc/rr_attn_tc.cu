@@ -435,12 +435,8 @@ int prefill_attn_make_maps(PrefillAttnArgs* a, long long q_rows, long long kv_ro
 }
 
 int launch_prefill_attn_tc(const PrefillAttnArgs& a, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(prefill_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess)
-            return RR_ERR_CUDA;
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr{0};
+    if (ensure_dyn_smem(prefill_attn_tc_kernel, (int)TC_SMEM, attr) != cudaSuccess) return RR_ERR_CUDA;
     const int n_work = ((a.max_len + TQ - 1) / TQ) * a.n_seqs * (a.n_heads / NH);
     const int grid = n_work < num_sms() ? n_work : num_sms();
     cudaError_t e = launch_pdl(prefill_attn_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TC_SMEM, st,

@@ -292,12 +292,8 @@ decode_chain_kernel(const __grid_constant__ ChainArgs a) {
 template <int BN>
 static int launch_chain_bn(const ChainArgs& a, cudaStream_t st) {
     constexpr int smem = GemmCfg<BN>::kSmemBytes + GemmCfg<BN>::kSiluStageBytes;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(decode_chain_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return RR_ERR_CUDA;
-        attr = true;
-    }
+    static std::atomic<uint64_t> attr{0};
+    if (ensure_dyn_smem(decode_chain_kernel<BN>, (int)smem, attr) != cudaSuccess) return RR_ERR_CUDA;
     cudaError_t e = launch_pdl(decode_chain_kernel<BN>, dim3(num_sms()), dim3(GEMM_THREADS), (size_t)smem, st, a);
     return (e == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }

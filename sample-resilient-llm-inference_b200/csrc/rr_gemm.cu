@@ -658,14 +658,16 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int l
     return r == CUDA_SUCCESS ? RR_OK : RR_ERR_CUDA;
 }
 
-static int g_num_sms = 0;
-int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+static std::atomic<int> g_num_sms[64];
+int num_sms() {                         // of the current device (one process may drive several)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = g_num_sms[dev & 63].load(std::memory_order_relaxed);
+    if (!n) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms[dev & 63].store(n, std::memory_order_relaxed);
     }
-    return g_num_sms;
+    return n;
 }
 
 // stream-K geometry: number of CTAs and of partial planes for [rowsA, K] weights.
@@ -690,13 +692,8 @@ template <int BN, int MODE>
 static int launch_one(const GemmPlan& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tcgen05<BN, MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN, MODE>());
-        if (e != cudaSuccess) return RR_ERR_CUDA;
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_set{0};
+    if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, MODE>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
     int grid;
     if (p.streamk) {
         grid = gemm_streamk_ctas(p.rowsA, p.K);
@@ -752,11 +749,8 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
 template <int MODE>
 static int launch_2cta(const GemmPlan& p, cudaStream_t st) {
     auto kern = gemm_bf16_tcgen05_2cta<MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM) != cudaSuccess) return RR_ERR_CUDA;
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_set{0};
+    if (ensure_dyn_smem(kern, (int)K2_SMEM, attr_set) != cudaSuccess) return RR_ERR_CUDA;
     const int pairs = (p.rowsA + 255) / 256, tilesB = (p.rowsB + K2_BN - 1) / K2_BN;
     int clusters = pairs * tilesB;
     if (clusters > num_sms() / 2) clusters = num_sms() / 2;

@@ -6,6 +6,8 @@
 // dependency (also inside CUDA-graph capture); launched normally both instructions are no-ops.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
 #include <utility>
 
 namespace rr {
@@ -50,6 +52,19 @@ __device__ __forceinline__ void trace_mark(int kid) {
 }
 __device__ __forceinline__ void trace_end(int slot) {
     if (slot >= 0) rr_trace_ptr[5 + 4 * slot] = rr_gtimer();
+}
+
+// cudaFuncSetAttribute applies to the current device only: one process may host several replicas (the HTTP gateway
+// runs one engine per GPU), so "already raised" is tracked per device (bit = device ordinal), lock-free.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 extern int g_use_pdl;   // rr_api.cu; env RR_NO_PDL=1 or rr_set_pdl(0) turns it off

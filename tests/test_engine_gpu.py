@@ -149,3 +149,27 @@ def test_run_batch_and_fault_injection():
         assert len(ok1) > 0
     finally:
         eng.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_replicas_in_one_process_agree():
+    """The HTTP gateway hosts one engine per GPU inside a single process: kernel attributes (dynamic shared memory
+    limits), SM counts and TMA maps must be set up per device.  Both replicas serve the same prompts concurrently
+    and must emit identical tokens (same weights, deterministic kernels)."""
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["small"]
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in (300, 64, 129, 17, 512, 255)]
+    engines = []
+    try:
+        for dev in (1, 0):           # the second device first: nothing may depend on "device 0 went first"
+            w = make_weights(spec, seed=5, sigma=0.03, device=f"cuda:{dev}", norm_jitter=0.1)
+            engines.append(Engine(w, device=dev, max_batch=8, ctx_max=640, max_prefill_tokens=1024))
+        tickets = [[e.submit(p, 12) for p in prompts] for e in engines]
+        outs = [[e.wait(t, timeout=120) for t in ts] for e, ts in zip(engines, tickets)]
+        assert all(r.status == 0 and len(r.tokens) == 12 for rs in outs for r in rs)
+        assert [r.tokens for r in outs[0]] == [r.tokens for r in outs[1]]
+    finally:
+        for e in engines:
+            e.close()
