@@ -115,6 +115,28 @@ def test_engine_backed_completion_and_batch():
     eng.close(); r.close()
 
 
+@pytest.mark.skipif(__import__("torch").cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_two_gpu_replicas_round_robin():
+    """The gateway layout of the reference (one server process, `start-gateway.sh:54`) with one replica per GPU:
+    a burst over a two-deployment group lands on both engines and every request decodes the same tokens."""
+    from rr_b200 import Engine, EngineBackend, Router, SPECS, make_weights
+    engs = []
+    for dev in (0, 1):
+        w = make_weights(SPECS["tiny"], seed=2, sigma=0.05, device=f"cuda:{dev}")
+        engs.append(Engine(w, device=dev, max_batch=8, ctx_max=256, max_prefill_tokens=512))
+    ml = [{"model_name": "chat", "litellm_params": {"model": f"b200/tiny@gpu{d}", "gpu": d}} for d in (0, 1)]
+    r = Router(model_list=ml, routing_strategy="round-robin", backends={d: EngineBackend(engs[d]) for d in (0, 1)})
+    try:
+        outs = r.completion_batch("chat", [list(range(7, 60))] * 10, 6)
+        assert not any(isinstance(o, Exception) for o in outs)
+        assert sorted(o.model for o in outs) == ["tiny@gpu0"] * 5 + ["tiny@gpu1"] * 5
+        assert all(o._token_ids == outs[0]._token_ids and len(o._token_ids) == 6 for o in outs)
+    finally:
+        for e in engs:
+            e.close()
+        r.close()
+
+
 def test_http_gateway_with_openai_sdk():
     import openai
     import uvicorn
