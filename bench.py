@@ -377,7 +377,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": DECODE_STEP_DRAM_BYTES_NCU if (args.model == "llama-3-8b" and C == 64 and P == 512 and M == 128) else None,
                          "traffic_source": "sum over the step's kernels of dram__bytes_read+write from ncu --set full (profiles/r01_ncu_full_summary.txt)",
-                         "kernel": "decode step = 1 CUDA-graph launch (228 kernels with PDL edges; dominant: gemm_bf16_tcgen05<64,*> weight stream)",
+                         "kernel": "decode step = 1 CUDA-graph launch (196 kernels with PDL edges; dominant: gemm_mlp_tcgen05<64> / gemm_bf16_tcgen05<64,*> weight streams)",
                          "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms, "peak_source": peak_src},
             "prefill": {"tflops": pf_tflops, "peak_tflops_sustained": tf_peak, "frac": (pf_tflops / tf_peak) if pf_tflops else None,
                         "ms_per_burst": mx[4].item() / K},

@@ -79,7 +79,7 @@ void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int 
 template <int THREADS, int MAXV>
 __global__ void __launch_bounds__(THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
-                   __nv_bfloat16* __restrict__ xn, int hidden, float eps) {
+                   __nv_bfloat16* __restrict__ xn, int hidden, float eps, unsigned* __restrict__ zero, int zero_n) {
     __shared__ float red[32];
     griddep_launch();
     const int tr_slot = trace_begin(TR_NORM);
@@ -94,6 +94,8 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
     }
     griddep_wait();
     trace_dep(tr_slot);
+    // optional: reset the dependency counters of the fused MLP kernel that follows (its previous user has completed)
+    if (zero_n > 0 && blockIdx.x == 0 && (int)threadIdx.x < zero_n) zero[threadIdx.x] = 0u;
     float4 v[MAXV];
     float ss = 0.f;
 #pragma unroll
@@ -134,14 +136,14 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
 }
 
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
-                        int hidden, float eps, cudaStream_t st) {
+                        int hidden, float eps, cudaStream_t st, unsigned* zero, int zero_n) {
     if (rows <= 0 || hidden > 8192) return;
     if (rows <= 256)
-        launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps);
+        launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
     else if (hidden <= 4096)      // fewer registers -> more rows in flight per SM (HBM-bound at thousands of rows)
-        launch_pdl(add_rmsnorm_kernel<256, 4>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps);
+        launch_pdl(add_rmsnorm_kernel<256, 4>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
     else
-        launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps);
+        launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
 }
 
 // ---- SiLU(gate) * up -----------------------------------------------------------------------------

@@ -127,6 +127,11 @@ struct rr_engine {
     std::vector<ChainArgs> chain;     // per layer
     unsigned* chain_counters = nullptr;   // [n_layers][8], zeroed at the start of every step
     bool fuse_silu = false;           // wgu interleaved + one gate/up plane: SiLU*mul lives in the GEMM epilogue
+    bool fuse_mlp = false;            // decode: gate/up and down GEMMs in one persistent launch (gemm_mlp_tcgen05)
+    std::vector<MlpPlan> mlp;         // per layer
+    MlpItem* mlp_items = nullptr;     // device copy of the schedule (shared by all layers)
+    unsigned* mlp_ready = nullptr;    // [n_slices] dependency counters, reset by the norm kernel before each launch
+    int mlp_slices = 0, mlp_slice_kb = 0;
     cudaGraphExec_t graph = nullptr;
     bool warmed = false;
 
@@ -232,12 +237,20 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
         // RoPE + KV append are fused into the attention kernel (reads the QKV split-K planes directly)
         launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
         if (gemm_launch(e->pl_o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        const void* nw = (l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm;
+        if (e->fuse_mlp) {
+            launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
+                               e->xn, B, d.hidden, d.rms_eps, s, e->mlp_ready, e->mlp_slices); ++nl;
+            if (mlp_launch(e->mlp[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+            launch_add_rmsnorm(e->x, part_f32(e->part_down, e->mlp_slices, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
+                               d.hidden, d.rms_eps, s); ++nl;
+            continue;
+        }
         launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
                            e->xn, B, d.hidden, d.rms_eps, s); ++nl;
         if (gemm_launch(e->pl_gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->fuse_silu) { launch_silu_mul(part_f32(e->part_gu, e->s_gu, B, 2 * d.inter), e->act, B, d.inter, s); ++nl; }
         if (gemm_launch(e->pl_down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
-        const void* nw = (l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm;
         launch_add_rmsnorm(e->x, part_f32(e->part_down, e->s_down, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
                            d.hidden, d.rms_eps, s); ++nl;
     }
@@ -579,7 +592,18 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRY(dalloc(e, &e->part_qkv, (size_t)e->s_qkv * B * e->nqkv));
     TRY(dalloc(e, &e->part_o, (size_t)e->s_o * B * d.hidden));
     TRY(dalloc(e, &e->part_gu, (size_t)e->s_gu * B * 2 * d.inter));
-    TRY(dalloc(e, &e->part_down, (size_t)e->s_down * B * d.hidden));
+    // fused decode MLP: the down GEMM's K range in <= 8 slices (one output plane each); 8 x 28 k-blocks for
+    // Llama-3-8B balances the per-CTA lists to within 5 % (see mlp_schedule)
+    {
+        const int kb1n = d.inter / 64;
+        int n_sl = (kb1n + 15) / 16;
+        n_sl = n_sl > 8 ? 8 : (n_sl < 1 ? 1 : n_sl);
+        e->mlp_slice_kb = (kb1n + n_sl - 1) / n_sl;
+        n_sl = (kb1n + e->mlp_slice_kb - 1) / e->mlp_slice_kb;
+        e->fuse_mlp = e->fuse_silu && opts->reserved[2] == 0 && d.inter % 64 == 0 && kb1n >= 1 && !getenv("RR_NO_MLP_FUSE");
+        e->mlp_slices = e->fuse_mlp ? n_sl : 0;
+    }
+    TRY(dalloc(e, &e->part_down, (size_t)(e->s_down > e->mlp_slices ? e->s_down : e->mlp_slices) * B * d.hidden));
     TRY(dalloc(e, &e->logits, (size_t)B * d.vocab));
     TRY(dalloc(e, &e->xn_last, (size_t)B * d.hidden));
     TRY(dalloc(e, &e->rope_table, (size_t)opts->ctx_max * 64));
@@ -675,6 +699,18 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
             c.x = e->x; c.xn = e->xn; c.rows = B; c.hidden = d.hidden; c.eps = d.rms_eps;
             c.counters = e->chain_counters + 8 * l;
         }
+    }
+    if (e->fuse_mlp) {
+        std::vector<MlpItem> sched;
+        const int grid = num_sms();
+        const int max_items = mlp_schedule(grid, d.inter, d.hidden, e->mlp_slice_kb, &sched);
+        TRY(dalloc(e, &e->mlp_items, sched.size()));
+        TRYC(cudaMemcpy(e->mlp_items, sched.data(), sched.size() * sizeof(MlpItem), cudaMemcpyHostToDevice));
+        TRY(dalloc(e, &e->mlp_ready, 8));
+        e->mlp.resize(L);
+        for (int l = 0; l < L; ++l)
+            TRY(mlp_plan_init(&e->mlp[l], e->wgu[l], e->wdown[l], d.inter, d.hidden, e->xn, B, e->act, e->part_down, B,
+                              e->bn_dec, e->mlp_items, max_items, grid, e->mlp_ready, e->mlp_slice_kb));
     }
     TRYC(cudaDeviceSynchronize());
     e->row_req.assign(B, nullptr);

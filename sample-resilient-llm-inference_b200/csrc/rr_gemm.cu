@@ -425,6 +425,183 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // =================================================================================================
+// Fused decode MLP: act = SiLU(x Wg^T) * (x Wu^T), planes = act Wd^T in ONE persistent launch (decode orientation,
+// weights on the UMMA M side).  Same warp roles, smem ring and TMEM double buffer as gemm_bf16_tcgen05; the pipeline
+// state simply carries from item to item.  Each CTA walks a host-built list: its gate/up tiles first, then its down
+// items.  A down item = (128 output features, one K-slice of `slice_kb` k-blocks); k-block kb of the down GEMM is
+// exactly the 64 act columns gate/up tile kb writes, so the item only depends on the tiles of its slice: the gate/up
+// epilogue bumps ready[slice] (release, gpu scope) and the producer of a down item requests the WEIGHT tiles of its
+// first stages, then acquires ready[slice] == slice length, then requests the activation tiles.  No kernel boundary,
+// no wave-quantisation tail of the gate/up grid (224 tiles on 148 SMs): CTAs that own one gate/up tile start on the
+// early slices while the others finish their second tile.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + kStages * Cfg::kStageBytesA;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* silu_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_launch();
+    const int tr_slot = trace_begin(TR_GEMM_DEC);
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&a.tmA0); tma_prefetch_desc(&a.tmB0);
+        tma_prefetch_desc(&a.tmA1); tma_prefetch_desc(&a.tmB1);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int4* my = reinterpret_cast<const int4*>(a.items) + (size_t)blockIdx.x * a.max_items;   // constant data
+    auto get = [&](int i, WorkItem& t, int& ph) -> bool {
+        if (i >= a.max_items) return false;
+        const int4 v = __ldg(my + i);
+        if (v.x < 0) return false;
+        ph = v.x >> 16; t.a_tile = v.x & 0xffff; t.b_tile = 0; t.kb0 = v.y; t.kb1 = v.z; t.z = v.w;
+        return true;
+    };
+    WorkItem t;
+    int ph = 0;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            const uint64_t polA = l2_policy_evict_first(), polB = l2_policy_evict_last();
+            int stage = 0;
+            uint32_t phase = 0;
+            bool first = true;
+            for (int i = 0; get(i, t, ph); ++i) {
+                const CUtensorMap* tA = ph ? &a.tmA1 : &a.tmA0;
+                const CUtensorMap* tB = ph ? &a.tmB1 : &a.tmB0;
+                // weight tiles of the first stages go out before the activations are known to exist: at the start
+                // of the kernel (PDL: the preceding kernel is still running) and for every down item (its slice of
+                // act may still be in flight on other SMs)
+                const int pre = (first || ph) ? min(kStages, t.kb1 - t.kb0) : 0;
+                const int st0 = stage;
+                for (int j = 0; j < pre; ++j) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, tA, &full_bar[stage], (t.kb0 + j) * BLOCK_K,
+                                     t.a_tile * BLOCK_A, polA);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (first) { griddep_wait(); trace_dep(tr_slot); first = false; }
+                if (ph) {
+                    const unsigned need = (unsigned)(t.kb1 - t.kb0);
+                    while (ld_acquire_gpu_u32(a.ready + t.z) < need) {
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> our TMA reads
+                }
+                for (int j = 0, s2 = st0; j < pre; ++j) {
+                    tma_load_2d_hint(smemB + s2 * Cfg::kStageBytesB, tB, &full_bar[s2], (t.kb0 + j) * BLOCK_K, 0, polB);
+                    if (++s2 == kStages) s2 = 0;
+                }
+                for (int kb = t.kb0 + pre; kb < t.kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, tA, &full_bar[stage], kb * BLOCK_K, t.a_tile * BLOCK_A, polA);
+                    tma_load_2d_hint(smemB + stage * Cfg::kStageBytesB, tB, &full_bar[stage], kb * BLOCK_K, 0, polB);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_A, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; get(it, t, ph); ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = t.kb0; kb < t.kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smemA + stage * Cfg::kStageBytesA));
+                    const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smemB + stage * Cfg::kStageBytesB));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;
+        RopeEpi no_rope;
+        no_rope.q_out = nullptr; no_rope.k_cache = nullptr; no_rope.v_cache = nullptr; no_rope.slot = nullptr;
+        no_rope.pos = nullptr; no_rope.table = nullptr; no_rope.n_heads = 0; no_rope.n_kv_heads = 0; no_rope.ctx_max = 0;
+        griddep_wait();
+        for (int it = 0; get(it, t, ph); ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tcgen05_fence_after();
+            const int a_row = t.a_tile * BLOCK_A + row_in_tile;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            if (ph == 0)
+                epilogue_item<BN, OUT_TRANSPOSED_SILU>(taddr0, a_row, t, quarter, lane, a.act, 2 * a.inter, a.rows, a.inter, 0,
+                                                       no_rope, silu_stage);
+            else
+                epilogue_item<BN, OUT_TRANSPOSED_F32>(taddr0, a_row, t, quarter, lane, a.out1, a.hidden, a.rows, a.hidden,
+                                                      a.ld_rows, no_rope, nullptr);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (ph == 0) {
+                // publish this tile's 64 act columns: every epilogue thread's stores, then one release-increment
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                if (etid == 0) {
+                    __threadfence();
+                    atomicAdd(a.ready + t.a_tile / a.slice_kb, 1u);
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    trace_end(tr_slot);
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// =================================================================================================
 // 2-CTA variant for the prefill orientation (tokens on M): a CTA pair (cluster of 2, same TPC) computes a
 // 256 x 256 tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its own 128 rows of A and only HALF of
 // the 256 B rows per k-block (the tensor core reads the other half from the peer's shared memory), so the smem fill
@@ -793,6 +970,78 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
         RR_CASE(256)
     }
 #undef RR_CASE
+    return RR_ERR_ARG;
+}
+
+
+// ---- fused decode MLP: host side ------------------------------------------------------------------
+// Greedy list schedule in units of k-blocks (+ a fixed per-item cost for pipeline refill / epilogue): gate/up tile t
+// goes to CTA t % grid (wave order: tile t is finished before tile t + grid); the down items, slice by slice (slices
+// become ready in that order), go to the least-loaded CTA.
+int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items) {
+    const int tiles0 = (2 * inter) / BLOCK_A, kb0n = (hidden + BLOCK_K - 1) / BLOCK_K;
+    const int tiles1 = (hidden + BLOCK_A - 1) / BLOCK_A, kb1n = inter / BLOCK_K;
+    const int n_slices = (kb1n + slice_kb - 1) / slice_kb;
+    constexpr int kItemCost = 6;
+    std::vector<std::vector<MlpItem>> per(grid);
+    std::vector<long long> load(grid, 0);
+    for (int t = 0; t < tiles0; ++t) {
+        MlpItem it; it.tile_phase = t; it.kb0 = 0; it.kb1 = kb0n; it.z = 0;
+        per[t % grid].push_back(it);
+        load[t % grid] += kb0n + kItemCost;
+    }
+    for (int z = 0; z < n_slices; ++z) {
+        const int k0 = z * slice_kb, k1 = (k0 + slice_kb < kb1n) ? k0 + slice_kb : kb1n;
+        for (int tl = 0; tl < tiles1; ++tl) {
+            int best = 0;
+            for (int c = 1; c < grid; ++c) if (load[c] < load[best]) best = c;
+            MlpItem it; it.tile_phase = tl | (1 << 16); it.kb0 = k0; it.kb1 = k1; it.z = z;
+            per[best].push_back(it);
+            load[best] += (k1 - k0) + kItemCost;
+        }
+    }
+    size_t mx = 1;
+    for (auto& v : per) mx = v.size() > mx ? v.size() : mx;
+    items->assign((size_t)grid * mx, MlpItem{-1, 0, 0, 0});
+    for (int c = 0; c < grid; ++c)
+        for (size_t i = 0; i < per[c].size(); ++i) (*items)[(size_t)c * mx + i] = per[c][i];
+    return (int)mx;
+}
+
+int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hidden, const void* xn, int rows,
+                  void* act, void* planes, int ld_rows, int bn, const MlpItem* items_dev, int max_items, int grid,
+                  unsigned* ready, int slice_kb) {
+    if (!p || !Wgu || !Wd || !xn || !act || !planes || !items_dev || !ready) return RR_ERR_ARG;
+    if (inter % 64 || (2 * inter) % BLOCK_A || hidden % 8 || rows > bn || bn < 32 || slice_kb < 1) return RR_ERR_ARG;
+    if ((2 * inter) / BLOCK_A > 0xffff || grid < 1 || grid > num_sms()) return RR_ERR_ARG;
+    MlpArgs& a = p->args;
+    int rc = make_tmap_bf16_2d(&a.tmA0, Wgu, 2 * inter, hidden, hidden, BLOCK_A);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a.tmB0, xn, rows, hidden, hidden, bn);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a.tmA1, Wd, hidden, inter, inter, BLOCK_A);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a.tmB1, act, rows, inter, inter, bn);
+    if (rc != RR_OK) return rc;
+    a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
+    a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
+    p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
+    return RR_OK;
+}
+
+template <int BN>
+static int launch_mlp_bn(const MlpPlan& p, cudaStream_t st) {
+    auto kern = gemm_mlp_tcgen05<BN>;
+    static std::atomic<uint64_t> attr_set{0};
+    if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
+    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), st, p.args);
+    return e == cudaSuccess ? RR_OK : RR_ERR_CUDA;
+}
+// Requires all CTAs co-resident (grid <= SM count; one CTA per SM by shared memory) and ready[] zero at launch.
+int mlp_launch(const MlpPlan& p, cudaStream_t st) {
+    switch (p.bn) {
+        case 32: return launch_mlp_bn<32>(p, st);
+        case 64: return launch_mlp_bn<64>(p, st);
+        case 128: return launch_mlp_bn<128>(p, st);
+        case 256: return launch_mlp_bn<256>(p, st);
+    }
     return RR_ERR_ARG;
 }
 

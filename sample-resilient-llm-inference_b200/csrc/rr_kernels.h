@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <vector>
 
 #include "../../include/rr_b200.h"
 
@@ -47,6 +48,37 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn);
 int gemm_launch(const GemmPlan& p, cudaStream_t st);
 
+// ---- fused decode MLP (rr_gemm.cu): gate/up GEMM (+SiLU*mul) and down GEMM in one persistent launch.
+// Per-CTA work lists (built once on the host) replace the kernel boundary: a down item covers one K-slice of
+// `slice_kb` k-blocks = the act columns written by `slice_kb` gate/up tiles, and waits for `ready[slice]` to reach
+// that count instead of for the whole gate/up grid.
+struct MlpItem {             // 16 bytes, read as int4
+    int tile_phase;           // a_tile | phase << 16 (phase 0 = gate/up, 1 = down); -1 terminates the list
+    int kb0, kb1;             // k-block range
+    int z;                    // down: output plane = K-slice index (also the index into `ready`)
+};
+struct MlpArgs {
+    CUtensorMap tmA0, tmB0;   // gate/up: weights [2*inter, hidden] (64-row interleaved), activations xn [rows, hidden]
+    CUtensorMap tmA1, tmB1;   // down: weights [hidden, inter], activations act [rows, inter]
+    __nv_bfloat16* act;       // [rows, inter]
+    float* out1;              // planes [n_slices][ld_rows][hidden]
+    int inter, hidden, rows, ld_rows;
+    const MlpItem* items;     // [grid][max_items]
+    int max_items;
+    unsigned* ready;          // [n_slices], zero at launch
+    int slice_kb;
+};
+struct MlpPlan {
+    MlpArgs args;
+    int grid, bn, n_slices;
+};
+// Host schedule: `items` gets grid * max_items entries (CTA-major); returns max_items.
+int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items);
+int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hidden, const void* xn, int rows,
+                  void* act, void* planes, int ld_rows, int bn, const MlpItem* items_dev, int max_items, int grid,
+                  unsigned* ready, int slice_kb);
+int mlp_launch(const MlpPlan& p, cudaStream_t st);
+
 // ---- persistent decode chain (rr_chain.cu): O GEMM -> norm -> gate/up GEMM -> down GEMM -> norm -> next GEMM
 struct ChainGemm {
     CUtensorMap tmA, tmB;     // A = weight [rowsA, K] (box 128 rows), B = activations [rows, K] (box bn rows)
@@ -86,8 +118,9 @@ struct PartIn {
 void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int rows, int hidden,
                   const int32_t* row_active, cudaStream_t st);
 // x[row] (+)= sum_z part[z][row]; xn[row] = rmsnorm(x[row]) * w   (part.ptr may be null: norm only)
+// `zero` (optional): zero_n (< 256) counters reset by the kernel, for the fused MLP kernel that follows it.
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
-                        int hidden, float eps, cudaStream_t st);
+                        int hidden, float eps, cudaStream_t st, unsigned* zero = nullptr, int zero_n = 0);
 // act[row, j] = silu(gate[row, j]) * up[row, j]; gate = cols [0, inter), up = cols [inter, 2*inter)
 void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st);
 // qkv (partials) -> RoPE(q), RoPE(k); q -> q_out [rows, n_heads*128] bf16; k, v -> KV cache.
