@@ -60,7 +60,10 @@ def test_engine_matches_hf_golden_tiny():
 
 
 @pytest.mark.parametrize("spec_name,max_batch", [("small", 16), ("small", 64), ("llama-3-8b-2l", 64), ("tiny96", 8),
-                                                 ("small96", 32), ("phi-3-mini-2l", 64), ("mistral-7b-2l", 64)])
+                                                 ("small96", 32), ("phi-3-mini-2l", 64), ("mistral-7b-2l", 64),
+                                                 # 128 / 256 decode rows: the BN = 128 / 256 instances of the decode
+                                                 # GEMMs and of the fused MLP kernel
+                                                 ("small", 128), ("small", 256)])
 def test_engine_matches_oracle(spec_name, max_batch):
     from oracle import llama_ref
     from rr_b200.models import SPECS, make_weights

@@ -188,3 +188,40 @@ def test_prefill_attention_causal_ragged(H, KV):
         ref = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(n, H * 128)
         got = out[int(start[s]):int(start[s]) + n].float()
         assert torch.allclose(got, ref, atol=3e-2, rtol=3e-2), (s, n, (got - ref).abs().max().item())
+
+
+def test_prefill_attention_rising_scores_rescale_path():
+    """tcgen05 prefill attention keeps O in TMEM and only raises a row's exponent reference when its running max
+    moved by more than 2^8; random scores never do.  Here every 64-key tile beats the previous one by > 2^8
+    (log2 domain), so every tile after the first takes the rescale path (TMEM ld / multiply / st of O)."""
+    lib = L()
+    H, KV, ctx_max, slots = 8, 2, 640, 3
+    lens = [512, 300, 129]
+    g = torch.Generator(device=DEV).manual_seed(5)
+    T = sum(lens)
+    start = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device=DEV, dtype=torch.int32)
+    seq_slot = torch.tensor([2, 0, 1], device=DEV, dtype=torch.int32)
+    q = torch.ones(T, H * 128, device=DEV).bfloat16()
+    q += (torch.randn(T, H * 128, device=DEV, generator=g) * 0.05).bfloat16()
+    step = 0.55 * (torch.arange(ctx_max, device=DEV) // 64).float()            # dot product jumps by ~70 per tile
+    kc = (step.view(1, 1, ctx_max, 1).expand(slots, KV, ctx_max, 128)
+          + torch.randn(slots, KV, ctx_max, 128, device=DEV, generator=g) * 0.02).bfloat16().contiguous()
+    vc = torch.randn(slots, KV, ctx_max, 128, device=DEV, generator=g).bfloat16()
+    out = torch.zeros(T, H * 128, device=DEV, dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(128)
+    lib.check(lib.lib.rr_op_prefill_attn(P(q), P(kc), P(vc), P(out), P(start), P(seq_slot), len(lens), max(lens), H, KV,
+                                         ctx_max, scale, None))
+    torch.cuda.synchronize()
+    G = H // KV
+    for s, n in enumerate(lens):
+        a0, sl = int(start[s]), int(seq_slot[s])
+        qs = q[a0:a0 + n].float().view(n, H, 128).transpose(0, 1)
+        k = kc[sl, :, :n].float().repeat_interleave(G, 0)
+        v = vc[sl, :, :n].float().repeat_interleave(G, 0)
+        sc = (qs @ k.transpose(1, 2)) * scale
+        sc = sc.masked_fill(~torch.ones(n, n, device=DEV, dtype=torch.bool).tril(), float("-inf"))
+        assert (sc[:, -1, 64:128].max() - sc[:, -1, :64].max()).item() * 1.4427 > 8.0 or n <= 64   # the jump is real
+        ref = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(n, H * 128)
+        got = out[a0:a0 + n].float()
+        assert torch.isfinite(got).all()
+        assert torch.allclose(got, ref, atol=3e-2, rtol=3e-2), (s, n, (got - ref).abs().max().item())
