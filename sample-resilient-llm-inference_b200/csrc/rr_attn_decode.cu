@@ -77,8 +77,10 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
         tma_prefetch_desc(&a.tmV);
     }
     __syncthreads();
-    griddep_wait();                         // slot/pos/q/KV come from the preceding kernels
-    trace_dep(tr_slot);
+    // Row metadata and the K/V rows of EARLIER tokens are constant for the whole step (written by previous graph
+    // launches; argmax bumps pos only at the very end of a step), so they may be read before the PDL wait: the producer
+    // gets the first ring of K/V tiles in flight while the QKV GEMM in front of this kernel is still draining.  Only q and
+    // the new token's k / v depend on that GEMM.
     const int slot = a.slot[row];
     if (slot < 0) return;
     const int ctx = a.pos[row] + 1;
@@ -106,6 +108,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
         const int first = min(RING, n_units);
         if (leader)
             for (int u = 0; u < first; ++u) issue(u);
+        griddep_wait();                         // q / new k / new v come from the QKV GEMM
         if (a.fuse_rope) {
             // K6 fused.  Rotated queries of the G heads -> smem (lane owns rotation pairs i = 2*lane, 2*lane+1 of
             // every head); if this CTA holds token `pos`: rotate the new key, append k / v (bf16) to the cache and
@@ -197,6 +200,8 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     }
 
     // ===================== consumers: warp w owns tokens [16w, 16w+16) of every tile =====================
+    griddep_wait();                             // a.q (unfused path) and `out` / `ws` ordering against the previous kernels
+    trace_dep(tr_slot);
     const int g = lane >> 2, t = lane & 3;
     // Q^T B-fragments: b0 = Q[head g][16ks + 2t, +1], b1 = Q[head g][16ks + 8 + 2t, +1]; heads >= G are zero
     uint32_t qb[8][2];
