@@ -13,13 +13,14 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int GROUP_A = 16;    // raster group: 16 A tiles share the streamed B tiles through L2
 
-template <int BN>
+// CAP bounds the smem ring (experiment knob RR_DEC_RING_CAP in rr_gemm.cu).
+template <int BN, int CAP = 8>
 struct GemmCfg {
     static constexpr int kStageBytesA = BLOCK_A * BLOCK_K * 2;
     static constexpr int kStageBytesB = BN * BLOCK_K * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kStages = kStagesRaw > CAP ? CAP : kStagesRaw;
     static constexpr uint32_t kTmemCols =
         (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -27,9 +28,9 @@ struct GemmCfg {
 };
 template <int MODE>
 __host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }
-template <int BN, int MODE>
+template <int BN, int MODE, int CAP = 8>
 constexpr int gemm_smem_bytes() {
-    return GemmCfg<BN>::kSmemBytes + (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN>::kSiluStageBytes : 0);
+    return GemmCfg<BN, CAP>::kSmemBytes + (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN, CAP>::kSiluStageBytes : 0);
 }
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.f + __expf(-g)) * u; }
 
