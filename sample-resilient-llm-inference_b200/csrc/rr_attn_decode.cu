@@ -82,7 +82,13 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     // gets the first ring of K/V tiles in flight while the QKV GEMM in front of this kernel is still draining.  Only q and
     // the new token's k / v depend on that GEMM.
     const int slot = a.slot[row];
-    if (slot < 0) return;
+    if (slot < 0) {
+        // inactive row.  Still wait: a grid none of whose CTAs executes griddepcontrol.wait would "complete" while its
+        // predecessor is running and break the completion chain the later kernels rely on (PDL ordering is transitive
+        // only through the waits).
+        griddep_wait();
+        return;
+    }
     const int ctx = a.pos[row] + 1;
     const int n_tiles_all = (ctx + DT - 1) / DT;
     const int tiles_per = (n_tiles_all + a.kv_splits - 1) / a.kv_splits;

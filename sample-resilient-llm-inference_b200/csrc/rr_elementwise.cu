@@ -79,7 +79,8 @@ void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int 
 template <int THREADS, int MAXV>
 __global__ void __launch_bounds__(THREADS)
 add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
-                   __nv_bfloat16* __restrict__ xn, int hidden, float eps, unsigned* __restrict__ zero, int zero_n) {
+                   __nv_bfloat16* __restrict__ xn, int hidden, float eps, unsigned* __restrict__ zero, int zero_n,
+                   float* __restrict__ rowss_out, int n_part_out) {
     __shared__ float red[32];
     griddep_launch();
     const int tr_slot = trace_begin(TR_NORM);
@@ -120,7 +121,10 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
         }
     }
     ss = block_sum(ss, red);
-    const float inv = rsqrtf(ss / (float)hidden + eps);
+    // deferred norm: hand sum(x^2) to the consuming GEMM's epilogue and leave the operand un-normalised
+    if (rowss_out != nullptr && (int)threadIdx.x < n_part_out)
+        rowss_out[(size_t)row * n_part_out + threadIdx.x] = threadIdx.x == 0 ? ss : 0.f;
+    const float inv = rowss_out != nullptr ? 1.f : rsqrtf(ss / (float)hidden + eps);
     __nv_bfloat16* out = xn + (size_t)row * hidden;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
@@ -136,14 +140,17 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
 }
 
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
-                        int hidden, float eps, cudaStream_t st, unsigned* zero, int zero_n) {
+                        int hidden, float eps, cudaStream_t st, unsigned* zero, int zero_n, float* rowss_out, int n_part_out) {
     if (rows <= 0 || hidden > 8192) return;
     if (rows <= 256)
-        launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
+        launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps, zero, zero_n,
+                   rowss_out, n_part_out);
     else if (hidden <= 4096)      // fewer registers -> more rows in flight per SM (HBM-bound at thousands of rows)
-        launch_pdl(add_rmsnorm_kernel<256, 4>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
+        launch_pdl(add_rmsnorm_kernel<256, 4>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n,
+                   rowss_out, n_part_out);
     else
-        launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n);
+        launch_pdl(add_rmsnorm_kernel<256, 8>, dim3(rows), dim3(256), 0, st, x, part, w, xn, hidden, eps, zero, zero_n,
+                   rowss_out, n_part_out);
 }
 
 // ---- SiLU(gate) * up -----------------------------------------------------------------------------

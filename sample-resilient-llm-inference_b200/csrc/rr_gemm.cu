@@ -38,6 +38,16 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
                                               void* __restrict__ out, int rowsA, int rowsB, int ldo, int ld_rows,
                                               const RopeEpi& rope, float* silu_stage) {
     constexpr int CH = (BN >= 32) ? 32 : 16;
+    // deferred RMSNorm, consumer side: this thread's row of the A operand was bf16(x * gamma); scale by 1 / rms(x)
+    float rinv = 1.f;
+    if constexpr (MODE == OUT_ROWMAJOR_ROPE || MODE == OUT_ROWMAJOR_SILU || MODE == OUT_ROWMAJOR_BF16) {
+        if (rope.n_part > 0 && a_row < rowsA) {
+            const float* ps = rope.rowss + (size_t)a_row * rope.n_part;
+            float ss = 0.f;
+            for (int j = 0; j < rope.n_part; ++j) ss += ps[j];
+            rinv = rsqrtf(ss * rope.inv_hidden + rope.eps);
+        }
+    }
     if constexpr (MODE == OUT_TRANSPOSED_SILU) {
         // gate/up rows are interleaved in blocks of 64: lanes 0..63 of the tile hold gate rows, lanes 64..127 the
         // matching up rows.  The up warps hand their values over through smem ([col][row] -> conflict-free), the
@@ -99,8 +109,8 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const float4 cs = *reinterpret_cast<const float4*>(tab + c + j + 2 * q);   // 2 pairs
-                                const float l0 = __uint_as_float(lo[j + 2 * q]), l1 = __uint_as_float(lo[j + 2 * q + 1]);
-                                const float h0 = __uint_as_float(hi[j + 2 * q]), h1 = __uint_as_float(hi[j + 2 * q + 1]);
+                                const float l0 = __uint_as_float(lo[j + 2 * q]) * rinv, l1 = __uint_as_float(lo[j + 2 * q + 1]) * rinv;
+                                const float h0 = __uint_as_float(hi[j + 2 * q]) * rinv, h1 = __uint_as_float(hi[j + 2 * q + 1]) * rinv;
                                 wl[q] = pack_bf16(l0 * cs.x - h0 * cs.y, l1 * cs.z - h1 * cs.w);
                                 wh[q] = pack_bf16(h0 * cs.x + l0 * cs.y, h1 * cs.z + l1 * cs.w);
                             }
@@ -121,10 +131,10 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 pk;
-                            pk.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                            pk.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            pk.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                            pk.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                            pk.x = pack_bf16(__uint_as_float(v[j + 0]) * rinv, __uint_as_float(v[j + 1]) * rinv);
+                            pk.y = pack_bf16(__uint_as_float(v[j + 2]) * rinv, __uint_as_float(v[j + 3]) * rinv);
+                            pk.z = pack_bf16(__uint_as_float(v[j + 4]) * rinv, __uint_as_float(v[j + 5]) * rinv);
+                            pk.w = pack_bf16(__uint_as_float(v[j + 6]) * rinv, __uint_as_float(v[j + 7]) * rinv);
                             *reinterpret_cast<uint4*>(dst + c + j) = pk;
                         }
                     }
@@ -133,6 +143,8 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
         }
     } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
         float* xres = reinterpret_cast<float*>(out);
+        const bool defer = rope.xhat != nullptr;       // also emit bf16(x * gamma) and sum(x^2) of this row over the tile
+        float ss = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
@@ -142,19 +154,43 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
             if (a_row < rowsA) {
                 float* dst = xres + (size_t)a_row * ldo + b0;
                 if (b0 + 32 <= rowsB) {
+                    __nv_bfloat16* hdst = defer ? rope.xhat + (size_t)a_row * ldo + b0 : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 32; j += 8) {
                         float4 x4 = *reinterpret_cast<const float4*>(dst + j);
+                        float4 y4 = *reinterpret_cast<const float4*>(dst + j + 4);
                         x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
                         x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
+                        y4.x += __uint_as_float(v[j + 4]); y4.y += __uint_as_float(v[j + 5]);
+                        y4.z += __uint_as_float(v[j + 6]); y4.w += __uint_as_float(v[j + 7]);
                         *reinterpret_cast<float4*>(dst + j) = x4;
+                        *reinterpret_cast<float4*>(dst + j + 4) = y4;
+                        if (defer) {
+                            const uint4 gw = *reinterpret_cast<const uint4*>(rope.gamma + b0 + j);
+                            ss += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w
+                                + y4.x * y4.x + y4.y * y4.y + y4.z * y4.z + y4.w * y4.w;
+                            uint4 pk;
+                            pk.x = pack_bf16(x4.x * bf16_lo(gw.x), x4.y * bf16_hi(gw.x));
+                            pk.y = pack_bf16(x4.z * bf16_lo(gw.y), x4.w * bf16_hi(gw.y));
+                            pk.z = pack_bf16(y4.x * bf16_lo(gw.z), y4.y * bf16_hi(gw.z));
+                            pk.w = pack_bf16(y4.z * bf16_lo(gw.w), y4.w * bf16_hi(gw.w));
+                            *reinterpret_cast<uint4*>(hdst + j) = pk;
+                        }
                     }
                 } else {
                     for (int j = 0; j < 32; ++j)
-                        if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
+                        if (b0 + j < rowsB) {
+                            const float xv = dst[j] + __uint_as_float(v[j]);
+                            dst[j] = xv;
+                            if (defer) {
+                                ss += xv * xv;
+                                rope.xhat[(size_t)a_row * ldo + b0 + j] = __float2bfloat16(xv * __bfloat162float(rope.gamma[b0 + j]));
+                            }
+                        }
                 }
             }
         }
+        if (defer && a_row < rowsA) rope.rowss_out[(size_t)a_row * rope.n_part_out + t.b_tile] = ss;
     } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
         // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
         // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
@@ -168,6 +204,13 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
                 tmem_ld_32x32b_x32(taddr0 + hb * 128 + c, vg);
                 tmem_ld_32x32b_x32(taddr0 + hb * 128 + 64 + c, vu);
                 tmem_ld_wait();
+                if (rope.n_part > 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        vg[j] = __float_as_uint(__uint_as_float(vg[j]) * rinv);
+                        vu[j] = __float_as_uint(__uint_as_float(vu[j]) * rinv);
+                    }
+                }
                 const int col = t.b_tile * (BN / 2) + hb * 64 + c;
                 if (a_row < rowsA) {
                     __nv_bfloat16* dst = act + (size_t)a_row * ldo + col;
@@ -208,6 +251,10 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
         tmem_ld_wait();
         const int b0 = t.b_tile * BN + c;
         if constexpr (MODE == OUT_ROWMAJOR_BF16) {
+            if (rope.n_part > 0) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rinv);
+            }
             if (a_row < rowsA) {
                 __nv_bfloat16* dst =
                     reinterpret_cast<__nv_bfloat16*>(out) + (size_t)a_row * ldo + b0;

@@ -29,6 +29,19 @@ struct RopeEpi {
     const int32_t* pos;
     const float2* table;      // [ctx_max][64] (cos, sin)
     int n_heads, n_kv_heads, ctx_max;
+    // ---- deferred RMSNorm (prefill): the GEMM that writes the residual also emits the next GEMM's operand
+    // xhat = bf16(x * gamma) (NOT normalised) and per-row partial sums of squares; the next GEMM scales its
+    // accumulators by rsqrt(mean(x^2) + eps) of the row in its epilogue (the projection is linear).  No norm kernel,
+    // no second pass over the fp32 residual.
+    // consumer side (OUT_ROWMAJOR_ROPE / _SILU / _BF16):
+    const float* rowss;       // [rowsA][n_part] partial sum(x^2) of the operand rows; n_part = 0: operand is normalised
+    int n_part;
+    float inv_hidden, eps;
+    // producer side (OUT_ROWMAJOR_RESID): xhat = nullptr -> plain residual add
+    const __nv_bfloat16* gamma;   // [rowsB] norm weight of the NEXT norm
+    __nv_bfloat16* xhat;          // [rowsA][ldo]
+    float* rowss_out;             // [rowsA][n_part_out], column = this item's b_tile
+    int n_part_out;
 };
 
 struct GemmPlan {
@@ -119,8 +132,11 @@ void launch_embed(const int32_t* ids, const __nv_bfloat16* table, float* x, int 
                   const int32_t* row_active, cudaStream_t st);
 // x[row] (+)= sum_z part[z][row]; xn[row] = rmsnorm(x[row]) * w   (part.ptr may be null: norm only)
 // `zero` (optional): zero_n (< 256) counters reset by the kernel, for the fused MLP kernel that follows it.
+// `rowss_out` (optional, deferred norm): write xn = bf16(x * w) UN-normalised and rowss_out[row][0] = sum(x^2),
+// rowss_out[row][1 .. n_part_out) = 0 -- the layout the OUT_ROWMAJOR_RESID epilogue produces (RopeEpi).
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
-                        int hidden, float eps, cudaStream_t st, unsigned* zero = nullptr, int zero_n = 0);
+                        int hidden, float eps, cudaStream_t st, unsigned* zero = nullptr, int zero_n = 0,
+                        float* rowss_out = nullptr, int n_part_out = 0);
 // act[row, j] = silu(gate[row, j]) * up[row, j]; gate = cols [0, inter), up = cols [inter, 2*inter)
 void launch_silu_mul(PartIn gu, __nv_bfloat16* act, int rows, int inter, cudaStream_t st);
 // qkv (partials) -> RoPE(q), RoPE(k); q -> q_out [rows, n_heads*128] bf16; k, v -> KV cache.

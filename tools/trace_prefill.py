@@ -22,17 +22,20 @@ a = np.frombuffer(buf, dtype=np.uint64)[: 4 * n.value].reshape(-1, 4).astype(np.
 a = a[np.argsort(a[:, 1])]
 print(f"{n.value} kernels; chunk span {(a[-1, 3] - a[0, 1]) / 1e6:.2f} ms")
 # per layer (after embed, norm0): qkv, rope, attn, o, norm, gu(+silu), down, norm
-names = ["gemm_qkv(+rope)", "attn", "gemm_o", "norm_mlp", "gemm_gate_up(+silu)", "gemm_down", "norm_next"]
+DEFER = bool(os.environ.get("RR_DEFER_NORM"))      # deferred RMSNorm (opt-in): no norm kernels inside the layers
+names = (["gemm_qkv(+rope,*rinv)", "attn", "gemm_o(+resid,xhat)", "gemm_gate_up(+silu,*rinv)", "gemm_down(+resid,xhat)"] if DEFER else
+         ["gemm_qkv(+rope)", "attn", "gemm_o", "norm_mlp", "gemm_gate_up(+silu)", "gemm_down", "norm_next"])
+PER = len(names)
 agg = {}
 for i in range(len(a) - 1):
     kid, s, d, e = a[i]
     seg = (a[i + 1, 2] - d) / 1e3
     if i < 2: nm = ["embed", "norm0"][i]
-    elif i < 2 + 7 * spec.n_layers: nm = names[(i - 2) % 7]
+    elif i < 2 + PER * spec.n_layers: nm = names[(i - 2) % PER]
     else: nm = "tail(" + NAMES.get(int(kid), str(kid)) + ")"
     x = agg.setdefault(nm, [0, 0.0, 0.0]); x[0] += 1; x[1] += seg; x[2] += (e - d) / 1e3
 tot = sum(v[1] for v in agg.values())
 for k, (c, seg, body) in sorted(agg.items(), key=lambda x: -x[1][1]):
-    print(f"{k:16s} n={c:3d}  critical {seg / 1e3:8.2f} ms  {100 * seg / tot:5.1f}%  avg {seg / c:8.1f} us  (CTA0 body {body / c:8.1f} us)")
+    print(f"{k:26s} n={c:3d}  critical {seg / 1e3:8.2f} ms  {100 * seg / tot:5.1f}%  avg {seg / c:8.1f} us  (CTA0 body {body / c:8.1f} us)")
 print(f"total {tot / 1e3:.2f} ms")
 eng.close()
