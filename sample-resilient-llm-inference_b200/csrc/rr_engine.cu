@@ -745,9 +745,20 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         TRYC(cudaMemcpy(e->mlp_items, sched.data(), sched.size() * sizeof(MlpItem), cudaMemcpyHostToDevice));
         TRY(dalloc(e, &e->mlp_ready, 8));
         e->mlp.resize(L);
-        for (int l = 0; l < L; ++l)
+        // experiment knob: RR_KV_PREFETCH_TILES = n -> the MLP kernel of layer l prefetches the first n K/V tiles per
+        // (row, kv head) of layer l + 1's attention into L2
+        const int pf_tiles = getenv("RR_KV_PREFETCH_TILES") ? atoi(getenv("RR_KV_PREFETCH_TILES")) : 0;
+        for (int l = 0; l < L; ++l) {
             TRY(mlp_plan_init(&e->mlp[l], e->wgu[l], e->wdown[l], d.inter, d.hidden, e->xn, B, e->act, e->part_down, B,
                               e->bn_dec, e->mlp_items, max_items, grid, e->mlp_ready, e->mlp_slice_kb));
+            if (pf_tiles > 0) {
+                const int ln = (l + 1) % L;                      // the last layer warms layer 0 of the next step
+                KvPrefetch& pf = e->mlp[l].args.pf;
+                pf.k = e->kcache + (size_t)ln * e->kv_layer_stride; pf.v = e->vcache + (size_t)ln * e->kv_layer_stride;
+                pf.slot = e->d_slot; pf.pos = e->d_pos; pf.rows = B; pf.n_kv_heads = d.n_kv_heads; pf.ctx_max = opts->ctx_max;
+                pf.tiles = pf_tiles;
+            }
+        }
     }
     TRYC(cudaDeviceSynchronize());
     e->row_req.assign(B, nullptr);

@@ -612,6 +612,25 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         RopeEpi no_rope;
         no_rope.q_out = nullptr; no_rope.k_cache = nullptr; no_rope.v_cache = nullptr; no_rope.slot = nullptr;
         no_rope.pos = nullptr; no_rope.table = nullptr; no_rope.n_heads = 0; no_rope.n_kv_heads = 0; no_rope.ctx_max = 0;
+        if (a.pf.k != nullptr) {
+            // These warps idle until the first accumulator is ready: use them to pull the first K/V tiles of the next
+            // attention kernel into L2 (one 16 KB piece per thread) while this kernel streams weights with evict_first.
+            const int per = 2 * a.pf.tiles;
+            const int id = (int)blockIdx.x * 128 + etid;
+            if (id < a.pf.rows * a.pf.n_kv_heads * per) {
+                const int rk = id / per, u = id - rk * per;
+                const int row = rk / a.pf.n_kv_heads, kvh = rk - row * a.pf.n_kv_heads;
+                const int slot = a.pf.slot[row];
+                const int tile = u >> 1;
+                const int ctx = slot >= 0 ? a.pf.pos[row] + 1 : 0;
+                const int n_tok = min(64, ctx - tile * 64);
+                if (n_tok > 0) {
+                    const __nv_bfloat16* base = (u & 1) ? a.pf.v : a.pf.k;
+                    const __nv_bfloat16* src = base + (((size_t)slot * a.pf.n_kv_heads + kvh) * a.pf.ctx_max + (size_t)tile * 64) * 128;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n_tok * 256) : "memory");
+                }
+            }
+        }
         griddep_wait();
         for (int it = 0; get(it, t, ph); ++it) {
             const int acc = it & 1;
@@ -1075,6 +1094,7 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
     if (rc != RR_OK) return rc;
     a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
     a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
+    memset(&a.pf, 0, sizeof(a.pf));
     p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
     return RR_OK;
 }

@@ -70,6 +70,16 @@ struct MlpItem {             // 16 bytes, read as int4
     int kb0, kb1;             // k-block range
     int z;                    // down: output plane = K-slice index (also the index into `ready`)
 };
+// L2 prefetch of the NEXT attention kernel's first K/V tiles, issued by the idle epilogue warps at the start of the
+// fused MLP kernel (earlier tokens' K/V rows are constant within a step, see rr_attn_decode.cu).
+struct KvPrefetch {
+    const __nv_bfloat16* k;   // next layer's K cache [slot][kv_head][ctx_max][128]; nullptr: off
+    const __nv_bfloat16* v;
+    const int32_t* slot;      // [rows]
+    const int32_t* pos;       // [rows]
+    int rows, n_kv_heads, ctx_max;
+    int tiles;                // 64-token tiles per (row, kv head) to prefetch, K and V each
+};
 struct MlpArgs {
     CUtensorMap tmA0, tmB0;   // gate/up: weights [2*inter, hidden] (64-row interleaved), activations xn [rows, hidden]
     CUtensorMap tmA1, tmB1;   // down: weights [hidden, inter], activations act [rows, inter]
@@ -80,6 +90,7 @@ struct MlpArgs {
     int max_items;
     unsigned* ready;          // [n_slices], zero at launch
     int slice_kb;
+    KvPrefetch pf;
 };
 struct MlpPlan {
     MlpArgs args;
