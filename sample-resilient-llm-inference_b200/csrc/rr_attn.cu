@@ -1,10 +1,11 @@
 // rr_attn.cu — attention over the slot-contiguous KV cache  [slot][kv_head][ctx_max][128] bf16.
 //
 //  * decode attention (K8) lives in rr_attn_decode.cu.
-//  * prefill_attn (K7): causal flash attention, 64 query rows x one head per CTA, bf16
-//    mma.sync.m16n8k16 with ldmatrix from XOR-swizzled shared memory.  (<1% of prefill FLOPs at
-//    512-token prompts — SURVEY.md §8d; the dense contraction of the path, the projections,
-//    runs on tcgen05 in rr_gemm.cu.)
+//  * prefill attention (K7) for even GQA group sizes runs on tcgen05 (rr_attn_tc.cu); launch_prefill_attn() below
+//    dispatches to it.
+//  * prefill_attn_kernel here: the mma.sync version -- causal flash attention, 64 query rows x one head per CTA, bf16
+//    mma.sync.m16n8k16 with ldmatrix from XOR-swizzled shared memory.  Serves MHA models (group size 1: the tcgen05
+//    kernel pairs two query heads on one kv head) and RR_NO_ATTN_TC=1.
 //
 // Replaces the remote bedrock:InvokeModel call (reference iam/policy.json:8).
 #include "rr_ptx.cuh"
