@@ -23,7 +23,10 @@ def run(e, new=48):
     recs, _ = e.run_batch(ids.reshape(-1), start, new)
     st = e.stats()
     return st["decode_ms_total"] / max(1, st["decode_steps"]), [r.tokens for r in recs]
-for e in (eng_a, eng_b): run(e, 8)
+run(eng_a, 8)                       # warm-up: captures the decode graph -- variant B also sees the variable here
+os.environ[var] = val
+run(eng_b, 8)
+os.environ.pop(var, None)
 ta, tb = [], []
 for _ in range(4):
     a, toks_a = run(eng_a); b, toks_b = run(eng_b)
