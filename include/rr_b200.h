@@ -50,6 +50,12 @@ int rr_set_pdl(int enabled);
  * (4 x uint64 each) to `out`. */
 int rr_debug_trace_start(int max_entries);
 int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n);
+/* Host-side work schedule of the fused decode MLP kernel (gate/up + down GEMMs in one launch), for
+ * inspection and tests; no device is touched.  items_out receives grid * (*max_items) entries of 4 x int32
+ * {tile | phase << 16 (phase 0 gate/up, 1 down; -1 = end of the CTA's list), kb0, kb1, slice}, CTA-major;
+ * returns RR_INVALID_ARGUMENT when `capacity` (in entries) is too small (*max_items is still set). */
+int rr_debug_mlp_schedule(int grid, int inter, int hidden, int slice_kb, int32_t* items_out, int capacity,
+                          int* max_items);
 
 /* ================================================================================================
  * 1. Router: admission + rpm/tpm bucket debit + backend pick + cooldown + fallback chain (K1).

@@ -208,6 +208,17 @@ RR_API int rr_op_decode_attn(const void* q, const void* k_cache, const void* v_c
     return check_last();
 }
 
+RR_API int rr_debug_mlp_schedule(int grid, int inter, int hidden, int slice_kb, int32_t* items_out, int capacity,
+                                 int* max_items) {
+    if (grid < 1 || inter < 64 || inter % 64 || hidden < 8 || slice_kb < 1 || !max_items) return RR_INVALID_ARGUMENT;
+    std::vector<MlpItem> items;
+    *max_items = mlp_schedule(grid, inter, hidden, slice_kb, &items);
+    if (!items_out || (size_t)capacity < items.size()) return RR_INVALID_ARGUMENT;
+    static_assert(sizeof(MlpItem) == 4 * sizeof(int32_t), "MlpItem layout");
+    memcpy(items_out, items.data(), items.size() * sizeof(MlpItem));
+    return RR_OK;
+}
+
 RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_cache, void* out,
                               const int32_t* seq_start, const int32_t* seq_slot, int n_seqs,
                               int max_len, int n_heads, int n_kv_heads, int ctx_max, float scale,
