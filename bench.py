@@ -383,6 +383,11 @@ def main():
                         "ms_per_burst": mx[4].item() / K},
             "clocks": clocks, "init_s": init_s, "weight_broadcast_s": bcast_s,
         }
+        # K1 (router kernel) is latency-bound, not roofline-bound: report time per event of a full trace
+        try:
+            line["router"] = router_kernel_timing(router)
+        except Exception as ex:                                   # never lose the headline line over the side measurement
+            line["router"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
             eng.close()
             v, sample, cores = cpu_port_sample(spec, P, M, C, world)
@@ -391,6 +396,44 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def router_kernel_timing(router, n_events: int = 2048, reps: int = 5):
+    """K1 alone: one launch over a trace of ADMIT + DONE pairs on the bench router (device buffers resident,
+    CUDA events on the launch stream) and the same trace through the host entry point (H2D + launch + D2H + sync)."""
+    import ctypes as C
+    import torch
+    from rr_b200 import _lib
+    n_dep = len(router.cfg.deployments)
+    now = router.now_ms()
+    ev = (_lib.Event * n_events)()
+    for i in range(0, n_events, 2):
+        ev[i] = _lib.Event(0, 0, 512, 0, now)                    # ADMIT to group 0
+        ev[i + 1] = _lib.Event(1, (i // 2) % n_dep, 128, 0, now)   # DONE on some deployment (keeps in-flight bounded)
+    out = (_lib.Decision * n_events)()
+    host = torch.frombuffer(bytearray(bytes(ev)), dtype=torch.uint8)
+    d_ev = host.cuda()
+    d_out = torch.empty(n_events * C.sizeof(_lib.Decision), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    def dev_once():
+        _lib.check(_lib.lib.rr_router_process_device(router._h, C.c_void_p(d_ev.data_ptr()), n_events,
+                                                     C.c_void_p(d_out.data_ptr()), C.c_void_p(stream.cuda_stream)))
+    for _ in range(2):
+        dev_once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        dev_once()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_ns = e0.elapsed_time(e1) * 1e6 / (reps * n_events)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        _lib.check(_lib.lib.rr_router_process(router._h, ev, n_events, out))
+    host_ns = (time.perf_counter() - t0) * 1e9 / (reps * n_events)
+    return {"events_per_launch": n_events, "ns_per_event_device": dev_ns, "events_per_s_device": 1e9 / dev_ns,
+            "ns_per_event_host_api": host_ns, "bound": "latency (one warp walks the trace in order; lanes = candidate deployments)"}
 
 
 if __name__ == "__main__":
