@@ -6,12 +6,12 @@
 // the result of one launch over an ordered event trace equals processing the events one by one).
 //
 // Design: router state (per-deployment window counters, in-flight counts, cooldown deadlines,
-// MT19937 stream, round-robin cursors) is resident in HBM.  The picks of one trace depend on each
+// MT19937 stream, round-robin cursors) is resident in HBM between launches and staged in shared memory for the
+// duration of one (router_kernel_smem; router_kernel keeps it in HBM for topologies that do not fit).  The picks of one trace depend on each
 // other through the RNG stream and the counters, so the trace is consumed by ONE warp in order;
 // the parallelism is across the <=32 candidate deployments of a model group: lane l owns
 // candidate l — eligibility is a ballot, the weighted pick is a rank-ordered scan + ballot
-// bisect, least-busy is a warp min-reduction.  Counter debits are atomics so that DONE events
-// posted from engine streams may race with admission without losing updates.
+// bisect, least-busy is a warp min-reduction.  Launches on one router are serialised (rr_router_process_device).
 // The RNG is CPython's: MT19937 with init_by_array seeding, random() = (a>>5, b>>6) 53-bit
 // doubles, _randbelow = getrandbits rejection loop (Lib/random.py:242-250, 454-489).
 // Latency/atomic-bound: not a roofline kernel; reported as ns/event.
@@ -19,6 +19,7 @@
 
 #include <mutex>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -116,20 +117,33 @@ struct WarpMT {
     }
 };
 
-__device__ __forceinline__ int nth_set_lane(uint32_t mask, int n) {   // n = 0-based rank
-    return __fns(mask, 0, n + 1);
+// position of the n-th (0-based) set bit of `mask`; the caller guarantees n < popc(mask).  Five popc steps instead of
+// __fns (a software loop): this sits on the dependent chain of every pick.
+__device__ __forceinline__ int nth_set_lane(uint32_t mask, int n) {
+    int pos = 0;
+    uint32_t m = mask;
+    int c = __popc(m & 0xFFFFu); if (n >= c) { n -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);       if (n >= c) { n -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);        if (n >= c) { n -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);        if (n >= c) { n -= c; pos += 2;  m >>= 2; }
+    if (n >= (int)(m & 1u)) pos += 1;
+    return pos;
 }
 
-__global__ void __launch_bounds__(32, 1)
-router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
-              rr_decision* __restrict__ decisions) {
-    __shared__ uint32_t s_mt[624];
+// State accessors: LOCAL = the arrays live in this CTA's shared memory for the duration of the launch (plain accesses);
+// otherwise they are in HBM (L2-coherent loads / stores, atomics for the debits).
+template <bool LOCAL, typename T> __device__ __forceinline__ T st_ld(const T* p) { return LOCAL ? *p : __ldcg(p); }
+template <bool LOCAL, typename T> __device__ __forceinline__ void st_st(T* p, T v) { if (LOCAL) *p = v; else __stcg(p, v); }
+template <bool LOCAL> __device__ __forceinline__ int st_add(int* p, int v) {
+    if (LOCAL) { const int o = *p; *p = o + v; return o; }
+    return atomicAdd(p, v);
+}
+
+// Walks events[0, n_events) in order (one warp).  `events` / `decisions` may be global or shared memory.
+template <bool LOCAL>
+__device__ __forceinline__ void run_trace(const RouterDev& S, WarpMT& rng, const rr_event* events, int n_events,
+                                          rr_decision* decisions) {
     const int lane = threadIdx.x;
-    for (int i = lane; i < 624; i += 32) s_mt[i] = S.mt[i];
-    WarpMT rng;
-    rng.mt = s_mt;
-    rng.mti = (int)S.mt[624];
-    __syncwarp();
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int e = 0; e < n_events; ++e) {
@@ -158,17 +172,17 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                     bool healthy = false;
                     if (valid) {
                         // roll the fixed one-minute window (bucket refill)
-                        if (__ldcg(&S.window[d]) != minute) {
-                            __stcg(&S.window[d], minute);
-                            __stcg(&S.req_count[d], 0);
-                            __stcg(&S.tok_count[d], 0);
+                        if (st_ld<LOCAL>(&S.window[d]) != minute) {
+                            st_st<LOCAL>(&S.window[d], (long long)minute);
+                            st_st<LOCAL>(&S.req_count[d], 0);
+                            st_st<LOCAL>(&S.tok_count[d], 0);
                         } else {
-                            req = __ldcg(&S.req_count[d]);
-                            tok = __ldcg(&S.tok_count[d]);
+                            req = st_ld<LOCAL>(&S.req_count[d]);
+                            tok = st_ld<LOCAL>(&S.tok_count[d]);
                         }
-                        infl = __ldcg(&S.inflight[d]);
+                        infl = st_ld<LOCAL>(&S.inflight[d]);
                         w = S.weight[d];
-                        healthy = now >= __ldcg(&S.cooldown_until[d]);
+                        healthy = now >= st_ld<LOCAL>(&S.cooldown_until[d]);
                         if (healthy && S.pre_call) {
                             const int rpm = S.rpm[d], tpm = S.tpm[d];
                             if (rpm >= 0 && req >= rpm) healthy = false;
@@ -221,16 +235,16 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                         if ((mask >> best) & 1u) pick_lane = best;
                         else uniform = true;
                     } else if (S.strategy == RR_STRATEGY_ROUND_ROBIN) {
-                        int k = __ldcg(&S.rr_next[grp]);
+                        int k = st_ld<LOCAL>(&S.rr_next[grp]);
                         __syncwarp();
-                        if (lane == 0) __stcg(&S.rr_next[grp], k + 1);
+                        if (lane == 0) st_st<LOCAL>(&S.rr_next[grp], k + 1);
                         pick_lane = nth_set_lane(mask, k % nh);
                     } else if (S.strategy == RR_STRATEGY_SPLIT) {
                         // contiguous shares of the declared burst: request i of N -> healthy[i * nh / N]
-                        const int n = __ldcg(&S.burst_size[grp]);
-                        const int i = __ldcg(&S.burst_pos[grp]);
+                        const int n = st_ld<LOCAL>(&S.burst_size[grp]);
+                        const int i = st_ld<LOCAL>(&S.burst_pos[grp]);
                         __syncwarp();
-                        if (lane == 0) __stcg(&S.burst_pos[grp], i + 1);
+                        if (lane == 0) st_st<LOCAL>(&S.burst_pos[grp], i + 1);
                         int idx = n > 0 ? (int)(((long long)i * nh) / n) : 0;
                         if (idx > nh - 1) idx = nh - 1;
                         pick_lane = nth_set_lane(mask, idx);
@@ -239,10 +253,10 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                     }
                     if (uniform) pick_lane = nth_set_lane(mask, (int)rng.randbelow((uint32_t)nh));
                     if (lane == pick_lane) {
-                        atomicAdd(&S.req_count[d], 1);
-                        atomicAdd(&S.tok_count[d], ev.tokens);
-                        atomicAdd(&S.inflight[d], 1);
-                        __stcg(&S.total_admitted[d], __ldcg(&S.total_admitted[d]) + 1);
+                        st_add<LOCAL>(&S.req_count[d], 1);
+                        st_add<LOCAL>(&S.tok_count[d], ev.tokens);
+                        st_add<LOCAL>(&S.inflight[d], 1);
+                        st_st<LOCAL>(&S.total_admitted[d], st_ld<LOCAL>(&S.total_admitted[d]) + 1ll);
                     }
                     dec.status = RR_OK;
                     dec.deployment = __shfl_sync(0xffffffffu, d, pick_lane);
@@ -259,7 +273,7 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
         } else if (ev.type == RR_EV_BURST) {
             const int g = ev.target;
             if (g >= 0 && g < S.n_groups) {
-                if (lane == 0) { __stcg(&S.burst_size[g], ev.tokens); __stcg(&S.burst_pos[g], 0); }
+                if (lane == 0) { st_st<LOCAL>(&S.burst_size[g], ev.tokens); st_st<LOCAL>(&S.burst_pos[g], 0); }
                 dec.status = RR_OK;
                 dec.served_group = g;
             }
@@ -269,23 +283,23 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
                 int cooled = 0;
                 if (lane == 0) {
                     int old = atomicSub(&S.inflight[d], 1);
-                    if (old <= 0) atomicAdd(&S.inflight[d], 1);   // clamp at 0
+                    if (old <= 0) st_add<LOCAL>(&S.inflight[d], 1);   // clamp at 0
                     if (ev.type == RR_EV_DONE) {
-                        if (__ldcg(&S.window[d]) != minute) {
-                            __stcg(&S.window[d], minute);
-                            __stcg(&S.req_count[d], 0);
-                            __stcg(&S.tok_count[d], 0);
+                        if (st_ld<LOCAL>(&S.window[d]) != minute) {
+                            st_st<LOCAL>(&S.window[d], (long long)minute);
+                            st_st<LOCAL>(&S.req_count[d], 0);
+                            st_st<LOCAL>(&S.tok_count[d], 0);
                         }
-                        atomicAdd(&S.tok_count[d], ev.tokens);
+                        st_add<LOCAL>(&S.tok_count[d], ev.tokens);
                     } else {
-                        if (__ldcg(&S.fail_window[d]) != minute) {
-                            __stcg(&S.fail_window[d], minute);
-                            __stcg(&S.fail_count[d], 0);
+                        if (st_ld<LOCAL>(&S.fail_window[d]) != minute) {
+                            st_st<LOCAL>(&S.fail_window[d], (long long)minute);
+                            st_st<LOCAL>(&S.fail_count[d], 0);
                         }
-                        int fc = __ldcg(&S.fail_count[d]) + 1;
-                        __stcg(&S.fail_count[d], fc);
+                        int fc = st_ld<LOCAL>(&S.fail_count[d]) + 1;
+                        st_st<LOCAL>(&S.fail_count[d], fc);
                         if (fc > S.allowed_fails) {
-                            __stcg(&S.cooldown_until[d], now + (long long)S.cooldown_ms);
+                            st_st<LOCAL>(&S.cooldown_until[d], now + (long long)S.cooldown_ms);
                             cooled = 1;
                         }
                     }
@@ -299,11 +313,114 @@ router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
         }
         if (lane == 0) decisions[e] = dec;
         __syncwarp();
-        __threadfence_block();
+        if (!LOCAL) __threadfence_block();
     }
     __syncwarp();
+}
+
+
+// ---- kernel, state in HBM (any topology) ----------------------------------------------------------
+__global__ void __launch_bounds__(32, 1)
+router_kernel(RouterDev S, const rr_event* __restrict__ events, int n_events,
+              rr_decision* __restrict__ decisions) {
+    __shared__ uint32_t s_mt[624];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 624; i += 32) s_mt[i] = S.mt[i];
+    WarpMT rng;
+    rng.mt = s_mt;
+    rng.mti = (int)S.mt[624];
+    __syncwarp();
+    run_trace<false>(S, rng, events, n_events, decisions);
     for (int i = lane; i < 624; i += 32) S.mt[i] = s_mt[i];
     if (lane == 0) S.mt[624] = (uint32_t)rng.mti;
+}
+
+// ---- kernel, state staged in shared memory ---------------------------------------------------------
+// A trace is a chain of dependent decisions, so what bounds it is the latency of every state access.  All mutable state
+// of a router is a few dozen bytes per deployment: this variant copies config + state into shared memory once, walks the
+// trace there (events and decisions move through shared memory in chunks of 128, loaded / stored by all lanes), and
+// writes the state back at the end.  Launches on one router are serialised by the library (stream order + an event
+// chain), which the MT19937 stream required anyway.
+constexpr int RT_CHUNK = 128;
+struct RouterSmemLayout {
+    uint32_t o_window, o_failw, o_cool, o_total, o_req, o_tok, o_failc, o_infl, o_rpm, o_tpm, o_wt, o_dgrp, o_gdeps,
+        o_goff, o_fboff, o_fbg, o_rr, o_bs, o_bp, o_mt, o_ev, o_dec, total;
+};
+__host__ __device__ inline RouterSmemLayout router_smem_layout(int n_deps, int n_groups, int n_fb) {
+    RouterSmemLayout L;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 15u) & ~15u; return o; };
+    L.o_window = take(8 * n_deps); L.o_failw = take(8 * n_deps); L.o_cool = take(8 * n_deps); L.o_total = take(8 * n_deps);
+    L.o_req = take(4 * n_deps); L.o_tok = take(4 * n_deps); L.o_failc = take(4 * n_deps); L.o_infl = take(4 * n_deps);
+    L.o_rpm = take(4 * n_deps); L.o_tpm = take(4 * n_deps); L.o_wt = take(4 * n_deps); L.o_dgrp = take(4 * n_deps);
+    L.o_gdeps = take(4 * n_deps);
+    L.o_goff = take(4 * (n_groups + 1)); L.o_fboff = take(4 * (n_groups + 1)); L.o_fbg = take(4 * (n_fb > 0 ? n_fb : 1));
+    L.o_rr = take(4 * n_groups); L.o_bs = take(4 * n_groups); L.o_bp = take(4 * n_groups);
+    L.o_mt = take(4 * 624);
+    L.o_ev = take(sizeof(rr_event) * RT_CHUNK); L.o_dec = take(sizeof(rr_decision) * RT_CHUNK);
+    L.total = off;
+    return L;
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_copy(T* dst, const T* src, int n) {
+    for (int i = threadIdx.x; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(32, 1)
+router_kernel_smem(RouterDev G, int n_fb, const rr_event* __restrict__ events, int n_events,
+                   rr_decision* __restrict__ decisions) {
+    extern __shared__ __align__(16) uint8_t rt_smem[];
+    const RouterSmemLayout L = router_smem_layout(G.n_deps, G.n_groups, n_fb);
+    const int lane = threadIdx.x, nd = G.n_deps, ng = G.n_groups;
+    RouterDev S = G;                                       // same scalars, pointers redirected into shared memory
+    long long* window = (long long*)(rt_smem + L.o_window); long long* failw = (long long*)(rt_smem + L.o_failw);
+    long long* cool = (long long*)(rt_smem + L.o_cool);     long long* total = (long long*)(rt_smem + L.o_total);
+    int* req = (int*)(rt_smem + L.o_req);   int* tok = (int*)(rt_smem + L.o_tok);
+    int* failc = (int*)(rt_smem + L.o_failc); int* infl = (int*)(rt_smem + L.o_infl);
+    int32_t* rpm = (int32_t*)(rt_smem + L.o_rpm); int32_t* tpm = (int32_t*)(rt_smem + L.o_tpm);
+    int32_t* wt = (int32_t*)(rt_smem + L.o_wt);   int32_t* dgrp = (int32_t*)(rt_smem + L.o_dgrp);
+    int32_t* gdeps = (int32_t*)(rt_smem + L.o_gdeps); int32_t* goff = (int32_t*)(rt_smem + L.o_goff);
+    int32_t* fboff = (int32_t*)(rt_smem + L.o_fboff); int32_t* fbg = (int32_t*)(rt_smem + L.o_fbg);
+    int* rrn = (int*)(rt_smem + L.o_rr); int* bs = (int*)(rt_smem + L.o_bs); int* bp = (int*)(rt_smem + L.o_bp);
+    uint32_t* s_mt = (uint32_t*)(rt_smem + L.o_mt);
+    rr_event* s_ev = (rr_event*)(rt_smem + L.o_ev); rr_decision* s_dec = (rr_decision*)(rt_smem + L.o_dec);
+
+    warp_copy(window, (const long long*)G.window, nd); warp_copy(failw, (const long long*)G.fail_window, nd);
+    warp_copy(cool, (const long long*)G.cooldown_until, nd); warp_copy(total, (const long long*)G.total_admitted, nd);
+    warp_copy(req, (const int*)G.req_count, nd); warp_copy(tok, (const int*)G.tok_count, nd);
+    warp_copy(failc, (const int*)G.fail_count, nd); warp_copy(infl, (const int*)G.inflight, nd);
+    warp_copy(rpm, G.rpm, nd); warp_copy(tpm, G.tpm, nd); warp_copy(wt, G.weight, nd); warp_copy(dgrp, G.dep_group, nd);
+    warp_copy(gdeps, G.group_deps, nd); warp_copy(goff, G.group_off, ng + 1); warp_copy(fboff, G.fb_off, ng + 1);
+    warp_copy(fbg, G.fb_groups, n_fb);
+    warp_copy(rrn, (const int*)G.rr_next, ng); warp_copy(bs, (const int*)G.burst_size, ng); warp_copy(bp, (const int*)G.burst_pos, ng);
+    warp_copy(s_mt, (const uint32_t*)G.mt, 624);
+    S.window = window; S.fail_window = failw; S.cooldown_until = cool; S.total_admitted = total;
+    S.req_count = req; S.tok_count = tok; S.fail_count = failc; S.inflight = infl;
+    S.rpm = rpm; S.tpm = tpm; S.weight = wt; S.dep_group = dgrp; S.group_deps = gdeps; S.group_off = goff;
+    S.fb_off = fboff; S.fb_groups = fbg; S.rr_next = rrn; S.burst_size = bs; S.burst_pos = bp;
+    WarpMT rng;
+    rng.mt = s_mt;
+    rng.mti = (int)G.mt[624];
+    __syncwarp();
+
+    constexpr int EW = sizeof(rr_event) / 4, DW = sizeof(rr_decision) / 4;
+    for (int base = 0; base < n_events; base += RT_CHUNK) {
+        const int n = min(RT_CHUNK, n_events - base);
+        warp_copy((uint32_t*)s_ev, (const uint32_t*)(events + base), n * EW);
+        __syncwarp();
+        run_trace<true>(S, rng, s_ev, n, s_dec);
+        warp_copy((uint32_t*)(decisions + base), (const uint32_t*)s_dec, n * DW);
+        __syncwarp();
+    }
+
+    warp_copy(G.window, (const long long*)window, nd); warp_copy(G.fail_window, (const long long*)failw, nd);
+    warp_copy(G.cooldown_until, (const long long*)cool, nd); warp_copy(G.total_admitted, (const long long*)total, nd);
+    warp_copy(G.req_count, (const int*)req, nd); warp_copy(G.tok_count, (const int*)tok, nd);
+    warp_copy(G.fail_count, (const int*)failc, nd); warp_copy(G.inflight, (const int*)infl, nd);
+    warp_copy(G.rr_next, (const int*)rrn, ng); warp_copy(G.burst_size, (const int*)bs, ng); warp_copy(G.burst_pos, (const int*)bp, ng);
+    warp_copy(G.mt, (const uint32_t*)s_mt, 624);
+    if (lane == 0) G.mt[624] = (uint32_t)rng.mti;
 }
 
 // ---------------------------------------------------------------- host side
@@ -343,6 +460,9 @@ struct rr_router {
     rr_event* d_events;
     rr_decision* d_dec;
     int cap;
+    int n_fb;               // fallback entries (layout of the shared-memory variant)
+    int smem_bytes;         // > 0: router_kernel_smem is usable (state fits in one CTA's shared memory)
+    cudaEvent_t last;       // completion of the latest launch: launches on one router are serialised across streams
     std::mutex mu;
 };
 
@@ -456,6 +576,16 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
 
     e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { rr::note_cuda_error(e); cudaFree(r->arena); delete r; return RR_CUDA_ERROR; }
+    e = cudaEventCreateWithFlags(&r->last, cudaEventDisableTiming);
+    if (e != cudaSuccess) { rr::note_cuda_error(e); cudaStreamDestroy(r->stream); cudaFree(r->arena); delete r; return RR_CUDA_ERROR; }
+    r->n_fb = n_fb;
+    r->smem_bytes = 0;
+    {
+        const RouterSmemLayout L = router_smem_layout(n_deps, n_groups, n_fb);
+        if (L.total <= 200 * 1024 && !getenv("RR_ROUTER_GLOBAL_STATE") &&
+            cudaFuncSetAttribute(router_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess)
+            r->smem_bytes = (int)L.total;
+    }
     int rc = ensure_cap(r, 1024);
     if (rc != RR_OK) { cudaStreamDestroy(r->stream); cudaFree(r->arena); delete r; return rc; }
     *out = r;
@@ -471,6 +601,7 @@ RR_API void rr_router_destroy(rr_router* r) {
     if (r->d_events) cudaFree(r->d_events);
     if (r->d_dec) cudaFree(r->d_dec);
     cudaFree(r->arena);
+    cudaEventDestroy(r->last);
     cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -479,8 +610,17 @@ RR_API int rr_router_process_device(rr_router* r, const rr_event* d_events, int 
                                     rr_decision* d_decisions, void* stream) {
     if (!r || n_events < 0 || (n_events && (!d_events || !d_decisions))) return RR_INVALID_ARGUMENT;
     if (n_events == 0) return RR_OK;
-    router_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(r->dev, d_events, n_events, d_decisions);
-    cudaError_t e = cudaGetLastError();
+    // one trace at a time per router: the RNG stream and (shared-memory variant) the staged state make launches
+    // order-dependent, so a launch on any stream first waits for the previous one
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaStreamWaitEvent(st, r->last, 0);
+    if (e != cudaSuccess) { rr::note_cuda_error(e); return RR_CUDA_ERROR; }
+    if (r->smem_bytes > 0)
+        router_kernel_smem<<<1, 32, r->smem_bytes, st>>>(r->dev, r->n_fb, d_events, n_events, d_decisions);
+    else
+        router_kernel<<<1, 32, 0, st>>>(r->dev, d_events, n_events, d_decisions);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(r->last, st);
     if (e != cudaSuccess) { rr::note_cuda_error(e); return RR_CUDA_ERROR; }
     return RR_OK;
 }
