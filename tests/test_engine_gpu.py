@@ -59,6 +59,29 @@ def test_engine_matches_hf_golden_tiny():
         eng.close()
 
 
+def test_engine_matches_hf_mistral_and_phi3_golden():
+    """Engine logits against the REAL transformers MistralForCausalLM / Phi3ForCausalLM outputs committed in
+    tests/golden/family_golden.pt (no oracle in between): GQA group size 2 on the tcgen05 attention path, and
+    MHA with head_dim 96 on the mma.sync path with the fused-projection layout HF Phi-3 uses."""
+    from test_oracle_llama import family_cases          # tests/ is on sys.path (pytest rootdir/conftest)
+    from rr_b200.engine import Engine
+    for fam, spec, w_cpu, prompts, logits, tokens in family_cases():
+        w = w_cpu.to("cuda")
+        eng = Engine(w, max_batch=8, ctx_max=256, max_prefill_tokens=512, use_cuda_graph=False)
+        try:
+            first, lg = eng.prefill(prompts, list(range(len(prompts))), want_logits=True)
+            for i, p in enumerate(prompts):
+                _cmp(lg[i], logits[i][0], f"{fam} prefill len={len(p)}")
+            # one teacher-forced decode step on HF's own first token
+            cur = [tk[0] for tk in tokens]
+            pos = [len(p) for p in prompts]
+            nxt, lg2 = eng.decode_step(list(range(len(prompts))), cur, pos, want_logits=True)
+            for i in range(len(prompts)):
+                _cmp(lg2[i], logits[i][1], f"{fam} decode seq {i}")
+        finally:
+            eng.close()
+
+
 @pytest.mark.parametrize("spec_name,max_batch", [("small", 16), ("small", 64), ("llama-3-8b-2l", 64), ("tiny96", 8),
                                                  ("small96", 32), ("phi-3-mini-2l", 64), ("mistral-7b-2l", 64),
                                                  # 128 / 256 decode rows: the BN = 128 / 256 instances of the decode
