@@ -220,3 +220,37 @@ def test_two_replicas_in_one_process_agree():
     finally:
         for e in engines:
             e.close()
+
+
+def test_generation_up_to_the_last_kv_slot_and_argument_bounds():
+    """Maximum sizes: prompt + max_new == ctx_max fills the KV slot to its last row (decode position ctx_max - 1);
+    one token more is rejected at submit, as are empty prompts and out-of-vocabulary ids."""
+    from oracle import llama_ref
+    from rr_b200 import _lib
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["tiny"]
+    w = make_weights(spec, seed=9, sigma=0.05, device="cuda", norm_jitter=0.1)
+    eng = Engine(w, max_batch=4, ctx_max=128, max_prefill_tokens=256)
+    try:
+        g = torch.Generator().manual_seed(2)
+        prompt = torch.randint(0, spec.vocab, (100,), generator=g).tolist()
+        rec = eng.wait(eng.submit(prompt, 28), timeout=60)              # 100 + 28 == ctx_max
+        assert rec.status == 0 and len(rec.tokens) == 28
+        # teacher-forced check of the LAST step (reads all 127 earlier rows, writes row 127)
+        ref = llama_ref.forward_logits(w, prompt + rec.tokens[:-1])[-1]
+        std = ref.std().item()
+        top2 = ref.topk(2).values
+        if (top2[0] - top2[1]).item() > 2 * TOL_MAX * std:
+            assert rec.tokens[-1] == int(ref.argmax())
+        with pytest.raises(Exception):
+            eng.submit(prompt, 29)                                       # would need row 128
+        with pytest.raises(Exception):
+            eng.submit([], 4)
+        with pytest.raises(Exception):
+            eng.submit([spec.vocab], 4)
+        # a second full-length request reuses the slot: same tokens (deterministic, no stale state)
+        rec2 = eng.wait(eng.submit(prompt, 28), timeout=60)
+        assert rec2.tokens == rec.tokens
+    finally:
+        eng.close()
