@@ -254,3 +254,35 @@ def test_generation_up_to_the_last_kv_slot_and_argument_bounds():
         assert rec2.tokens == rec.tokens
     finally:
         eng.close()
+
+
+def test_long_prompts_match_oracle():
+    """3000- and 1500-token prompts in one prefill chunk (47 / 24 key tiles per query tile in the tcgen05 attention
+    kernel, deep online-softmax chains), then decode steps at context ~3000 (47 K/V tiles per row in the decode
+    attention kernel)."""
+    from oracle import llama_ref
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["small"]
+    w = make_weights(spec, seed=13, sigma=0.03, device="cuda", norm_jitter=0.1)
+    eng = Engine(w, max_batch=4, ctx_max=3072, max_prefill_tokens=4608, use_cuda_graph=False)
+    try:
+        g = torch.Generator().manual_seed(8)
+        lens = [3000, 1500]
+        prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in lens]
+        first, logits = eng.prefill(prompts, [1, 3], want_logits=True)
+        w_cpu = w.to("cpu")
+        for i, p in enumerate(prompts):
+            _cmp(logits[i], llama_ref.forward_logits(w_cpu, p)[-1], f"long prefill len={lens[i]}")
+        toks = [list(p) for p in prompts]
+        cur = [int(t) for t in first]
+        for j in range(2):
+            pos = [len(t) for t in toks]
+            for t, c in zip(toks, cur):
+                t.append(c)
+            nxt, lg = eng.decode_step([1, 3], cur, pos, want_logits=True)
+            for i in range(2):
+                _cmp(lg[i], llama_ref.forward_logits(w_cpu, toks[i])[-1], f"long decode step {j} seq {i}")
+            cur = [int(t) for t in nxt]
+    finally:
+        eng.close()
