@@ -201,6 +201,16 @@ static int pick_splits(int N, int K) {
     return s;
 }
 
+// One engine at a time per device.  The fused MLP kernel (and the experimental chain kernel) are persistent grids whose
+// CTAs spin on work of sibling CTAs; two such grids interleaved on one GPU (two engines, two streams) could each hold
+// SMs the other's not-yet-resident CTAs need.  Every path below synchronises its stream before it releases this lock, so
+// engines that share a device alternate at prefill-chunk / decode-step granularity.  (The gateway creates one engine per
+// GPU, so this lock is uncontended there.)
+static std::mutex& device_mutex(int dev) {
+    static std::mutex mu[64];
+    return mu[dev & 63];
+}
+
 static PartIn part_f32(const float* p, int splits, int rows, int ld) {
     PartIn r; r.ptr = p; r.is_bf16 = 0; r.n_splits = splits; r.split_stride = (long long)rows * ld; r.ld = ld;
     return r;
@@ -502,6 +512,7 @@ static void worker_main(rr_engine* e) {
             e->st.active_rows = active;
         }
         std::lock_guard<std::mutex> gl(e->gpu_mu);
+        std::lock_guard<std::mutex> dl(device_mutex(e->o.device));
         if (!chunk.empty()) {
             int rc = run_prefill(e, ids.data(), seq_start.data(), slots.data(), (int)chunk.size(), nullptr, nullptr);
             const double t = now_s(e);
@@ -792,6 +803,7 @@ RR_API int rr_engine_prefill(rr_engine* e, const int32_t* ids, const int32_t* se
                              int n_seqs, int32_t* first_tok, float* logits_out) {
     if (!e || !ids || !seq_start || !slots || n_seqs < 1) return RR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> gl(e->gpu_mu);
+    std::lock_guard<std::mutex> dl(device_mutex(e->o.device));
     CK(cudaSetDevice(e->o.device));
     return run_prefill(e, ids, seq_start, slots, n_seqs, first_tok, logits_out);
 }
@@ -800,6 +812,7 @@ RR_API int rr_engine_decode_step(rr_engine* e, const int32_t* slots, const int32
                                  int32_t* next_tok, float* logits_out) {
     if (!e || !slots || !tok || !pos || n < 1 || n > e->Bm || !next_tok) return RR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> gl(e->gpu_mu);
+    std::lock_guard<std::mutex> dl(device_mutex(e->o.device));
     CK(cudaSetDevice(e->o.device));
     const int B = e->Bm;
     int32_t* h = e->h_stage;                 // tok[B] | pos[B] | slot[B]

@@ -286,3 +286,24 @@ def test_long_prompts_match_oracle():
             cur = [int(t) for t in nxt]
     finally:
         eng.close()
+
+
+def test_two_engines_on_one_device_run_concurrently():
+    """Two engines that share a GPU (e.g. two model groups mapped to one device through the C-ABI) serve at the same
+    time from their own worker threads.  Their persistent kernels (fused MLP: CTAs spin on sibling CTAs' tiles) must
+    never be interleaved on the device -- the library alternates them per prefill chunk / decode step."""
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS["small"]
+    w = make_weights(spec, seed=17, sigma=0.03, device="cuda", norm_jitter=0.1)
+    g = torch.Generator().manual_seed(3)
+    prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in (200, 64, 31, 400, 129, 257)]
+    engines = [Engine(w, max_batch=32, ctx_max=640, max_prefill_tokens=1024) for _ in range(2)]
+    try:
+        tickets = [[e.submit(p, 24) for p in prompts] for e in engines]         # both workers busy at once
+        outs = [[e.wait(t, timeout=120) for t in ts] for e, ts in zip(engines, tickets)]
+        assert all(r.status == 0 and len(r.tokens) == 24 for rs in outs for r in rs)
+        assert [r.tokens for r in outs[0]] == [r.tokens for r in outs[1]]
+    finally:
+        for e in engines:
+            e.close()
