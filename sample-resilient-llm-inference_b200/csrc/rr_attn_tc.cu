@@ -1,5 +1,5 @@
 // rr_attn_tc.cu — prefill attention (K7) on tcgen05: causal flash attention with both contractions on
-// the 5th-gen tensor cores, S and per-tile O in TMEM, K/V tiles staged by TMA.
+// the 5th-gen tensor cores, S, P and the O accumulator in TMEM, Q / K / V tiles staged by TMA.
 //
 // Persistent kernel, one CTA per SM, 12 warps = 3 warpgroups (one warp of each per SM sub-partition):
 //   warp 0      TMA producer  : Q tiles (128 rows x 128 dims, two query heads that share a kv head) and a
