@@ -144,53 +144,102 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
     } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
         float* xres = reinterpret_cast<float*>(out);
         const bool defer = rope.xhat != nullptr;       // also emit bf16(x * gamma) and sum(x^2) of this row over the tile
-        float ss = 0.f;
+        if (!defer && silu_stage != nullptr) {
+            // Coalesced residual add.  TMEM hands every thread one ROW (32 consecutive columns = one 128-byte line per
+            // chunk), so a direct read-modify-write issues 16-byte pieces of 32 different lines per instruction: 32 LSU
+            // wavefronts and half-used sectors.  Each warp instead transposes its 32 x 32 chunk through 4.5 KB of shared
+            // memory (row pitch 36 floats: conflict-free both ways) and lets 8 lanes cover one line: 4 full lines per
+            // instruction.
+            float* stg = silu_stage + (quarter * 32) * 36;              // this warp's [32][36] tile
+            const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
+            const int row0 = t.a_tile * BLOCK_A + quarter * 32;         // first of this warp's 32 rows
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr0 + c, v);
-            tmem_ld_wait();
-            const int b0 = t.b_tile * BN + c;
-            if (a_row < rowsA) {
-                float* dst = xres + (size_t)a_row * ldo + b0;
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr0 + c, v);
+                tmem_ld_wait();
+                const int b0 = t.b_tile * BN + c;
                 if (b0 + 32 <= rowsB) {
-                    __nv_bfloat16* hdst = defer ? rope.xhat + (size_t)a_row * ldo + b0 : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float4 x4 = *reinterpret_cast<const float4*>(dst + j);
-                        float4 y4 = *reinterpret_cast<const float4*>(dst + j + 4);
-                        x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
-                        x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
-                        y4.x += __uint_as_float(v[j + 4]); y4.y += __uint_as_float(v[j + 5]);
-                        y4.z += __uint_as_float(v[j + 6]); y4.w += __uint_as_float(v[j + 7]);
-                        *reinterpret_cast<float4*>(dst + j) = x4;
-                        *reinterpret_cast<float4*>(dst + j + 4) = y4;
-                        if (defer) {
-                            const uint4 gw = *reinterpret_cast<const uint4*>(rope.gamma + b0 + j);
-                            ss += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w
-                                + y4.x * y4.x + y4.y * y4.y + y4.z * y4.z + y4.w * y4.w;
-                            uint4 pk;
-                            pk.x = pack_bf16(x4.x * bf16_lo(gw.x), x4.y * bf16_hi(gw.x));
-                            pk.y = pack_bf16(x4.z * bf16_lo(gw.y), x4.w * bf16_hi(gw.y));
-                            pk.z = pack_bf16(y4.x * bf16_lo(gw.z), y4.y * bf16_hi(gw.z));
-                            pk.w = pack_bf16(y4.z * bf16_lo(gw.w), y4.w * bf16_hi(gw.w));
-                            *reinterpret_cast<uint4*>(hdst + j) = pk;
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    __syncwarp();
+                    // all eight loads first: a store between them would fence the later loads (possible aliasing) and
+                    // turn eight independent L2 round trips into a chain
+                    float4 xs[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + sub_row;
+                        xs[i] = (row0 + r < rowsA) ? *reinterpret_cast<const float4*>(xres + (size_t)(row0 + r) * ldo + b0 + sub_col)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + sub_row;
+                        if (row0 + r < rowsA) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(stg + r * 36 + sub_col);
+                            float4 x4 = xs[i];
+                            x4.x += a4.x; x4.y += a4.y; x4.z += a4.z; x4.w += a4.w;
+                            *reinterpret_cast<float4*>(xres + (size_t)(row0 + r) * ldo + b0 + sub_col) = x4;
                         }
                     }
-                } else {
+                    __syncwarp();
+                } else if (a_row < rowsA) {
+                    float* dst = xres + (size_t)a_row * ldo + b0;
                     for (int j = 0; j < 32; ++j)
-                        if (b0 + j < rowsB) {
-                            const float xv = dst[j] + __uint_as_float(v[j]);
-                            dst[j] = xv;
-                            if (defer) {
-                                ss += xv * xv;
-                                rope.xhat[(size_t)a_row * ldo + b0 + j] = __float2bfloat16(xv * __bfloat162float(rope.gamma[b0 + j]));
-                            }
-                        }
+                        if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
                 }
             }
+        } else {
+            float ss = 0.f;
+    #pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr0 + c, v);
+                tmem_ld_wait();
+                const int b0 = t.b_tile * BN + c;
+                if (a_row < rowsA) {
+                    float* dst = xres + (size_t)a_row * ldo + b0;
+                    if (b0 + 32 <= rowsB) {
+                        __nv_bfloat16* hdst = defer ? rope.xhat + (size_t)a_row * ldo + b0 : nullptr;
+    #pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float4 x4 = *reinterpret_cast<const float4*>(dst + j);
+                            float4 y4 = *reinterpret_cast<const float4*>(dst + j + 4);
+                            x4.x += __uint_as_float(v[j + 0]); x4.y += __uint_as_float(v[j + 1]);
+                            x4.z += __uint_as_float(v[j + 2]); x4.w += __uint_as_float(v[j + 3]);
+                            y4.x += __uint_as_float(v[j + 4]); y4.y += __uint_as_float(v[j + 5]);
+                            y4.z += __uint_as_float(v[j + 6]); y4.w += __uint_as_float(v[j + 7]);
+                            *reinterpret_cast<float4*>(dst + j) = x4;
+                            *reinterpret_cast<float4*>(dst + j + 4) = y4;
+                            if (defer) {
+                                const uint4 gw = *reinterpret_cast<const uint4*>(rope.gamma + b0 + j);
+                                ss += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w
+                                    + y4.x * y4.x + y4.y * y4.y + y4.z * y4.z + y4.w * y4.w;
+                                uint4 pk;
+                                pk.x = pack_bf16(x4.x * bf16_lo(gw.x), x4.y * bf16_hi(gw.x));
+                                pk.y = pack_bf16(x4.z * bf16_lo(gw.y), x4.w * bf16_hi(gw.y));
+                                pk.z = pack_bf16(y4.x * bf16_lo(gw.z), y4.y * bf16_hi(gw.z));
+                                pk.w = pack_bf16(y4.z * bf16_lo(gw.w), y4.w * bf16_hi(gw.w));
+                                *reinterpret_cast<uint4*>(hdst + j) = pk;
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (b0 + j < rowsB) {
+                                const float xv = dst[j] + __uint_as_float(v[j]);
+                                dst[j] = xv;
+                                if (defer) {
+                                    ss += xv * xv;
+                                    rope.xhat[(size_t)a_row * ldo + b0 + j] = __float2bfloat16(xv * __bfloat162float(rope.gamma[b0 + j]));
+                                }
+                            }
+                    }
+                }
+            }
+            if (defer && a_row < rowsA) rope.rowss_out[(size_t)a_row * rope.n_part_out + t.b_tile] = ss;
         }
-        if (defer && a_row < rowsA) rope.rowss_out[(size_t)a_row * rope.n_part_out + t.b_tile] = ss;
     } else if constexpr (MODE == OUT_ROWMAJOR_SILU) {
         // BN == 256 weight rows = [gate 64 | up 64 | gate 64 | up 64]: a token's gate and up values sit in the same
         // TMEM lane, so silu(g) * u needs no exchange; 128 output columns per tile, ldo = inter.
@@ -680,7 +729,8 @@ constexpr int K2_STAGE_A = BLOCK_A * BLOCK_K * 2;          // 16 KB: this CTA's 
 constexpr int K2_STAGE_B = 128 * BLOCK_K * 2;              // 16 KB: this CTA's half of the 256 B rows
 constexpr int K2_STAGE = K2_STAGE_A + K2_STAGE_B;
 constexpr int K2_STAGES = 6;
-constexpr int K2_SMEM = K2_STAGES * K2_STAGE + 1024 + 256;
+constexpr int K2_EPI_STAGE = 4 * 32 * 36 * 4;             // residual epilogue: per-warp 32 x 36 fp32 transpose tiles
+constexpr int K2_SMEM = K2_STAGES * K2_STAGE + 1024 + 256 + K2_EPI_STAGE;
 constexpr int GROUP_PAIRS = 8;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -852,7 +902,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
             t.a_tile = pa * 2 + (int)rank; t.b_tile = tb; t.z = 0; t.kb0 = 0; t.kb1 = kblocks;
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * K2_BN;
-            epilogue_item<K2_BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, 0, rope, nullptr);
+            epilogue_item<K2_BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, 0, rope,
+                                       reinterpret_cast<float*>(smem + K2_STAGES * K2_STAGE + 256));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(empty0_remote + acc * 8);

@@ -30,7 +30,9 @@ template <int MODE>
 __host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }
 template <int BN, int MODE, int CAP = 8>
 constexpr int gemm_smem_bytes() {
-    return GemmCfg<BN, CAP>::kSmemBytes + (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN, CAP>::kSiluStageBytes : 0);
+    // SILU (decode): up-row exchange; RESID (prefill): per-warp 32 x 36 fp32 transpose tiles (18 KB) -- same slot
+    return GemmCfg<BN, CAP>::kSmemBytes +
+           (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN, CAP>::kSiluStageBytes : MODE == OUT_ROWMAJOR_RESID ? 4 * 32 * 36 * 4 : 0);
 }
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.f + __expf(-g)) * u; }
 
