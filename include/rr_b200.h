@@ -233,7 +233,7 @@ typedef struct rr_engine_opts {
     int32_t fail_seed;            /* fault injection: seed of the Bernoulli failure mask */
     float fail_prob;              /* fault injection: P(request fails) (BASELINE config #4) */
     int32_t reserved[4];          /* A/B switches: [0] = 1 no persistent chain kernel; [1] = 1 no RoPE fusion in the prefill
-                                     QKV epilogue; [2] = 1 no fused decode MLP kernel; [3] = 1 prefill RMSNorm deferred into the GEMM epilogues (measured slower, off by default) */
+                                     QKV epilogue; [2] = 1 no fused decode MLP kernel; [3] = 1 prefill RMSNorm as separate kernels instead of deferred into the GEMM epilogues */
 } rr_engine_opts;
 
 int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w,

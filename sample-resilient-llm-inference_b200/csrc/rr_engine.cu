@@ -715,11 +715,10 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                        d.vocab, B, 1, OUT_TRANSPOSED_F32, e->bn_dec));
     e->fuse_rope_pf = d.head_dim == 128 && opts->reserved[1] == 0;
     e->pf_parts = (d.hidden + 255) / 256;
-    // Opt-in (reserved[3] = 1 or RR_DEFER_NORM=1).  Measured with tools/prefill_ab.py (two engines alternating in one
-    // process): 90.5 ms vs 89.3 ms per 8192-token chunk -- the heavier residual epilogues (o-proj +35 %) cost more than
-    // the two 62 us norm kernels they replace.  Kept because it is parity-tested and the trade-off flips once the
-    // residual epilogue stops being the slow part of the O projection.
-    e->defer_norm_pf = (opts->reserved[3] == 1 || getenv("RR_DEFER_NORM")) && d.hidden % 8 == 0 && e->pf_parts <= 64;
+    // On by default (reserved[3] = 1 or RR_NO_DEFER_NORM=1 restores the two norm kernels per layer).  In-process A/B
+    // (tools/prefill_ab.py): 91.0 -> 85.2 ms per 8192-token chunk once the residual epilogue became line-coalesced;
+    // with the earlier row-per-thread epilogue the same fusion LOST 1.4 % (o-proj +35 %).
+    e->defer_norm_pf = opts->reserved[3] == 0 && !getenv("RR_NO_DEFER_NORM") && d.hidden % 8 == 0 && e->pf_parts <= 64;
     if (e->defer_norm_pf) TRY(dalloc(e, &e->p_rowss, (size_t)e->Tmax * e->pf_parts));
     e->use_chain = e->fuse_silu && opts->reserved[0] == 0 && e->bn_dec >= 32;
     if (e->use_chain) {

@@ -144,7 +144,7 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
     } else if constexpr (MODE == OUT_ROWMAJOR_RESID) {
         float* xres = reinterpret_cast<float*>(out);
         const bool defer = rope.xhat != nullptr;       // also emit bf16(x * gamma) and sum(x^2) of this row over the tile
-        if (!defer && silu_stage != nullptr) {
+        if (silu_stage != nullptr) {
             // Coalesced residual add.  TMEM hands every thread one ROW (32 consecutive columns = one 128-byte line per
             // chunk), so a direct read-modify-write issues 16-byte pieces of 32 different lines per instruction: 32 LSU
             // wavefronts and half-used sectors.  Each warp instead transposes its 32 x 32 chunk through 4.5 KB of shared
@@ -153,6 +153,9 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
             float* stg = silu_stage + (quarter * 32) * 36;              // this warp's [32][36] tile
             const int sub_row = lane >> 3, sub_col = (lane & 7) * 4;
             const int row0 = t.a_tile * BLOCK_A + quarter * 32;         // first of this warp's 32 rows
+            float ssr[8];                                               // deferred norm: sum(x^2) pieces of rows 4i + sub_row
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ssr[i] = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t v[32];
@@ -182,13 +185,51 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
                             float4 x4 = xs[i];
                             x4.x += a4.x; x4.y += a4.y; x4.z += a4.z; x4.w += a4.w;
                             *reinterpret_cast<float4*>(xres + (size_t)(row0 + r) * ldo + b0 + sub_col) = x4;
+                            if (defer) {
+                                const uint2 gw = *reinterpret_cast<const uint2*>(rope.gamma + b0 + sub_col);
+                                ssr[i] += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w;
+                                uint2 pk;
+                                pk.x = pack_bf16(x4.x * bf16_lo(gw.x), x4.y * bf16_hi(gw.x));
+                                pk.y = pack_bf16(x4.z * bf16_lo(gw.y), x4.w * bf16_hi(gw.y));
+                                *reinterpret_cast<uint2*>(rope.xhat + (size_t)(row0 + r) * ldo + b0 + sub_col) = pk;
+                            }
                         }
                     }
                     __syncwarp();
-                } else if (a_row < rowsA) {
-                    float* dst = xres + (size_t)a_row * ldo + b0;
-                    for (int j = 0; j < 32; ++j)
-                        if (b0 + j < rowsB) dst[j] += __uint_as_float(v[j]);
+                } else {
+                    // ragged last chunk: thread = row, scalar; its sum(x^2) joins the row's lane group through smem
+                    float ss_tail = 0.f;
+                    if (a_row < rowsA) {
+                        float* dst = xres + (size_t)a_row * ldo + b0;
+                        for (int j = 0; j < 32; ++j)
+                            if (b0 + j < rowsB) {
+                                const float xv = dst[j] + __uint_as_float(v[j]);
+                                dst[j] = xv;
+                                if (defer) {
+                                    ss_tail += xv * xv;
+                                    rope.xhat[(size_t)a_row * ldo + b0 + j] = __float2bfloat16(xv * __bfloat162float(rope.gamma[b0 + j]));
+                                }
+                            }
+                    }
+                    if (defer) {
+                        stg[lane * 36] = ss_tail;                     // row `lane` of this warp
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if ((lane & 7) == 0) ssr[i] += stg[(4 * i + sub_row) * 36];
+                        __syncwarp();
+                    }
+                }
+            }
+            if (defer) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v2 = ssr[i];
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+                    const int r = row0 + 4 * i + sub_row;
+                    if ((lane & 7) == 0 && r < rowsA) rope.rowss_out[(size_t)r * rope.n_part_out + t.b_tile] = v2;
                 }
             }
         } else {

@@ -177,23 +177,24 @@ def test_run_batch_and_fault_injection():
         eng.close()
 
 
-def test_deferred_norm_prefill_option_matches_oracle():
-    """Opt-in prefill variant without norm kernels: the residual epilogues emit bf16(x * gamma) and sum(x^2), the next
-    GEMM's epilogue applies 1 / rms (RopeEpi in csrc/rr_kernels.h).  Same tolerance as the default path."""
+def test_separate_norm_kernels_prefill_option_matches_oracle():
+    """The default prefill defers RMSNorm into the GEMM epilogues (residual epilogues emit bf16(x * gamma) and sum(x^2),
+    the next GEMM's epilogue applies 1 / rms; RopeEpi in csrc/rr_kernels.h) -- every other test here runs that path.
+    This one covers the fallback with two norm kernels per layer (defer_norm=False).  Same tolerance."""
     from oracle import llama_ref
     from rr_b200.models import SPECS, make_weights
     from rr_b200.engine import Engine
     for name in ("small", "small96"):                     # fused-RoPE epilogue / bf16 epilogue + rope kernel
         spec = SPECS[name]
         w = make_weights(spec, seed=3, sigma=0.03, device="cuda", norm_jitter=0.1)
-        eng = Engine(w, max_batch=16, ctx_max=640, max_prefill_tokens=2048, use_cuda_graph=False, defer_norm=True)
+        eng = Engine(w, max_batch=16, ctx_max=640, max_prefill_tokens=2048, use_cuda_graph=False, defer_norm=False)
         try:
             g = torch.Generator().manual_seed(5)
             lens = [3, 64, 129, 300, 512]
             prompts = [torch.randint(0, spec.vocab, (n,), generator=g).tolist() for n in lens]
             first, logits = eng.prefill(prompts, [15, 0, 5, 2, 3], want_logits=True)
             for i, p in enumerate(prompts):
-                _cmp(logits[i], llama_ref.forward_logits(w, p)[-1], f"deferred-norm prefill {name} len={lens[i]}")
+                _cmp(logits[i], llama_ref.forward_logits(w, p)[-1], f"separate-norm prefill {name} len={lens[i]}")
         finally:
             eng.close()
 

@@ -7,7 +7,7 @@ import torch
 from rr_b200.models import SPECS, make_weights
 from rr_b200.engine import Engine
 
-var = sys.argv[1] if len(sys.argv) > 1 else "RR_DEFER_NORM"
+var = sys.argv[1] if len(sys.argv) > 1 else "RR_NO_DEFER_NORM"
 spec = SPECS["llama-3-8b"]
 w = make_weights(spec, seed=0, device="cuda")
 os.environ.pop(var, None)
