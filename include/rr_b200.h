@@ -35,7 +35,8 @@ enum {
     RR_INVALID_ARGUMENT = 4,
     RR_CUDA_ERROR = 5,
     RR_TIMEOUT = 6,
-    RR_BACKEND_FAILED = 7     /* injected/real backend failure with no fallback left -> 500 */
+    RR_BACKEND_FAILED = 7,    /* injected/real backend failure with no fallback left -> 500 */
+    RR_CANCELLED = 8          /* the request was abandoned by its owner (rr_engine_cancel / rr_gateway_cancel) */
 };
 
 const char* rr_version(void);
@@ -56,6 +57,12 @@ int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n);
  * returns RR_INVALID_ARGUMENT when `capacity` (in entries) is too small (*max_items is still set). */
 int rr_debug_mlp_schedule(int grid, int inter, int hidden, int slice_kb, int32_t* items_out, int capacity,
                           int* max_items);
+
+/* Host-side work schedule of the persistent decode layer kernel (O -> gate/up -> down -> next projection in one launch,
+ * DESIGN.md section 3): same entry format with phase 0 = O (slice = split-K plane), 1 = gate/up, 2 = down (slice = K-slice),
+ * 3 = next projection (QKV of the next layer / lm_head; slice = split-K plane).  has_main = 0: phase 3 only. */
+int rr_debug_layer_schedule(int grid, int hidden, int inter, int nq, int rows_a3, int s_o, int s3, int slice_kb,
+                            int has_main, int32_t* items_out, int capacity, int* max_items);
 
 /* ================================================================================================
  * 1. Router: admission + rpm/tpm bucket debit + backend pick + cooldown + fallback chain (K1).
@@ -232,7 +239,7 @@ typedef struct rr_engine_opts {
     int32_t use_cuda_graph;       /* capture the decode step */
     int32_t fail_seed;            /* fault injection: seed of the Bernoulli failure mask */
     float fail_prob;              /* fault injection: P(request fails) (BASELINE config #4) */
-    int32_t reserved[4];          /* A/B switches: [0] = 1 no persistent chain kernel; [1] = 1 no RoPE fusion in the prefill
+    int32_t reserved[4];          /* A/B switches: [0] = 1 no persistent decode layer kernel (rr_layer.cu); [1] = 1 no RoPE fusion in the prefill
                                      QKV epilogue; [2] = 1 no fused decode MLP kernel; [3] = 1 prefill RMSNorm as separate kernels instead of deferred into the GEMM epilogues */
 } rr_engine_opts;
 
@@ -267,6 +274,10 @@ int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int 
                      uint64_t* ticket);
 int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_completion* out,
                    int32_t* tokens_out, int max_tokens_out);
+/* Abandon a request: queued -> dropped; running -> its decode row is freed at the next step; finished -> freed.
+ * Consumes the ticket (do not wait on it afterwards).  Replaces the client-side `timeout=` of the reference's
+ * chat.completions.create calls (reference src/demo_fallback.py:146) as seen from the backend. */
+int rr_engine_cancel(rr_engine* e, uint64_t ticket);
 /* Streaming (SSE): block until the request holds more than `have` tokens, is done, or `timeout_s` elapses;
  * copies the tokens generated so far.  Does not consume the request — finish with rr_engine_wait. */
 int rr_engine_peek(rr_engine* e, uint64_t ticket, int have, double timeout_s, int32_t* tokens_out,
@@ -287,6 +298,74 @@ typedef struct rr_engine_stats {
 } rr_engine_stats;
 int rr_engine_get_stats(rr_engine* e, rr_engine_stats* out);
 int rr_engine_reset_stats(rr_engine* e);
+
+/* ================================================================================================
+ * 5. Gateway: the whole per-request path behind one submit / wait pair, in native code.
+ *    Replaces the reference's gateway process as its clients see it: N concurrent blocking
+ *    chat.completions.create calls (reference src/demo_load_balancing.py:195-203,
+ *    src/demo_quota_isolation.py:135-139) into litellm's single worker (reference bin/start-gateway.sh:54).
+ *    rr_gateway_submit is thread-safe and non-blocking: the request enters an admission queue; a dispatcher
+ *    thread coalesces everything pending (ADMIT / DONE / FAIL / fallback re-ADMIT) into ONE ordered trace per
+ *    K1 launch (rr_router_process) and hands admitted prompts straight to the engine of the picked
+ *    deployment.  A backend failure walks the fallback chain inside the library. */
+
+typedef struct rr_gateway rr_gateway;
+
+typedef struct rr_gateway_opts {
+    int32_t manual_clock;      /* 0: events are stamped with the wall clock (ms); 1: with rr_gateway_set_now() */
+    int32_t record_trace;      /* keep the last N (event, decision) pairs for replay through an oracle; 0 = off */
+    int32_t max_batch_events;  /* events per K1 launch, 0 = 4096 */
+    int32_t reserved[5];
+} rr_gateway_opts;
+
+typedef struct rr_gateway_result {
+    uint64_t ticket;
+    int32_t status;            /* RR_OK / RR_RATE_LIMITED (429) / RR_NO_GROUP / RR_BACKEND_FAILED / RR_TIMEOUT / RR_CANCELLED / ...;
+                                  -1 while in flight (rr_gateway_peek) */
+    int32_t deployment, served_group, chain_pos, replica;   /* the admission decision (valid once admitted) */
+    int32_t n_prompt, n_generated;
+    int32_t attempts;          /* admissions this request went through (1 + backends that failed under it) */
+    double t_submit_s, t_admit_s, t_first_token_s, t_done_s;   /* gateway monotonic clock, seconds */
+} rr_gateway_result;
+
+typedef struct rr_gateway_stats {
+    uint64_t submitted, admitted, completed, rate_limited, failed, failed_over;
+    uint64_t launches;         /* K1 launches */
+    uint64_t events;           /* events those launches processed */
+    uint64_t max_batch;        /* largest trace of one launch */
+    uint64_t in_flight;
+    double admit_wait_s;       /* sum over admissions of (decision time - submit time) */
+} rr_gateway_stats;
+
+/* engines[i] serves the deployments whose rr_deployment_desc.replica == replica_ids[i].  The router and the engines
+ * must outlive the gateway; the engines' completion hooks are taken by the gateway until it is destroyed. */
+int rr_gateway_create(rr_router* router, rr_engine* const* engines, const int32_t* replica_ids, int n_engines,
+                      const rr_gateway_opts* opts, rr_gateway** out);
+void rr_gateway_destroy(rr_gateway* g);
+int rr_gateway_set_now(rr_gateway* g, int64_t now_ms);
+/* group = index of the model group (model_name) the client asked for.  Returns RR_NO_GROUP / RR_INVALID_ARGUMENT
+ * (prompt + max_new_tokens beyond a replica's context, bad token id: HTTP 400) before anything is debited. */
+int rr_gateway_submit(rr_gateway* g, int group, const int32_t* prompt_ids, int n_prompt, int max_new_tokens,
+                      uint64_t* ticket);
+/* A closed burst as one contiguous block of the admission trace (declare_burst != 0 prepends RR_EV_BURST). */
+int rr_gateway_submit_batch(rr_gateway* g, int group, const int32_t* prompt_ids, const int32_t* prompt_start, int n,
+                            int max_new_tokens, int declare_burst, uint64_t* tickets);
+/* Blocks (release the GIL) until the request is finished; returns its status and consumes the ticket.
+ * RR_TIMEOUT: still in flight -- wait again or rr_gateway_cancel. */
+int rr_gateway_wait(rr_gateway* g, uint64_t ticket, double timeout_s, rr_gateway_result* out, int32_t* tokens_out,
+                    int max_tokens_out);
+/* Streaming: returns once more than `have` tokens exist, the request is finished, or timeout_s elapsed. */
+int rr_gateway_peek(rr_gateway* g, uint64_t ticket, int have, double timeout_s, int32_t* tokens_out, int max_tokens_out,
+                    int32_t* n_generated, int32_t* done, rr_gateway_result* out);
+/* Abandon a request (consumes the ticket).  count_as_failure != 0: a client-side timeout -- the deployment gets a FAIL
+ * event (allowed_fails / cooldown, reference config/config.yaml:103-104); 0: a disconnect -- a DONE event. */
+int rr_gateway_cancel(rr_gateway* g, uint64_t ticket, int count_as_failure);
+/* Block until every event queued so far (the DONE / FAIL reports of finished requests included) has been through K1:
+ * call before rr_router_snapshot when the counters must reflect all completed requests. */
+int rr_gateway_quiesce(rr_gateway* g, double timeout_s);
+int rr_gateway_get_stats(rr_gateway* g, rr_gateway_stats* out);
+/* The recorded trace (opts.record_trace): *n pairs, oldest first. */
+int rr_gateway_trace(rr_gateway* g, rr_event* events, rr_decision* decisions, int capacity, int* n);
 
 #ifdef __cplusplus
 }

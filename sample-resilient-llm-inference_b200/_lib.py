@@ -95,6 +95,23 @@ class EngineStats(C.Structure):
                 ("queued", C.c_int32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class GatewayOpts(C.Structure):
+    _fields_ = [("manual_clock", C.c_int32), ("record_trace", C.c_int32), ("max_batch_events", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+class GatewayResult(C.Structure):
+    _fields_ = [("ticket", C.c_uint64), ("status", C.c_int32), ("deployment", C.c_int32), ("served_group", C.c_int32),
+                ("chain_pos", C.c_int32), ("replica", C.c_int32), ("n_prompt", C.c_int32), ("n_generated", C.c_int32),
+                ("attempts", C.c_int32), ("t_submit_s", C.c_double), ("t_admit_s", C.c_double),
+                ("t_first_token_s", C.c_double), ("t_done_s", C.c_double)]
+
+
+class GatewayStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("submitted", "admitted", "completed", "rate_limited", "failed", "failed_over",
+                                          "launches", "events", "max_batch", "in_flight")] + [("admit_wait_s", C.c_double)]
+
+
 # ---------------------------------------------------------------- prototypes
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/rr_b200.h.
 PROTOTYPES = {
@@ -105,6 +122,7 @@ PROTOTYPES = {
     "rr_debug_trace_start": (C.c_int, [C.c_int]),
     "rr_debug_trace_stop": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, c_i32p]),
     "rr_debug_mlp_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p]),
+    "rr_debug_layer_schedule": (C.c_int, [C.c_int] * 9 + [c_i32p, C.c_int, c_i32p]),
     "rr_router_create": (C.c_int, [C.POINTER(DeploymentDesc), C.c_int, C.c_int, c_i32p, c_i32p,
                                    C.POINTER(RouterSettings), C.c_uint64, C.c_int,
                                    C.POINTER(vp)]),
@@ -146,6 +164,19 @@ PROTOTYPES = {
     "rr_engine_now": (C.c_double, [vp]),
     "rr_engine_get_stats": (C.c_int, [vp, C.POINTER(EngineStats)]),
     "rr_engine_reset_stats": (C.c_int, [vp]),
+    "rr_engine_cancel": (C.c_int, [vp, C.c_uint64]),
+    "rr_gateway_create": (C.c_int, [vp, C.POINTER(vp), c_i32p, C.c_int, C.POINTER(GatewayOpts), C.POINTER(vp)]),
+    "rr_gateway_destroy": (None, [vp]),
+    "rr_gateway_set_now": (C.c_int, [vp, C.c_int64]),
+    "rr_gateway_submit": (C.c_int, [vp, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "rr_gateway_submit_batch": (C.c_int, [vp, C.c_int, c_i32p, c_i32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "rr_gateway_wait": (C.c_int, [vp, C.c_uint64, C.c_double, C.POINTER(GatewayResult), c_i32p, C.c_int]),
+    "rr_gateway_peek": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_double, c_i32p, C.c_int, c_i32p, c_i32p,
+                                  C.POINTER(GatewayResult)]),
+    "rr_gateway_cancel": (C.c_int, [vp, C.c_uint64, C.c_int]),
+    "rr_gateway_quiesce": (C.c_int, [vp, C.c_double]),
+    "rr_gateway_get_stats": (C.c_int, [vp, C.POINTER(GatewayStats)]),
+    "rr_gateway_trace": (C.c_int, [vp, C.POINTER(Event), C.POINTER(Decision), C.c_int, c_i32p]),
 }
 
 MISSING = []

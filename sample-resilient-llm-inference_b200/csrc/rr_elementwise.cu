@@ -96,7 +96,8 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
     griddep_wait();
     trace_dep(tr_slot);
     // optional: reset the dependency counters of the fused MLP kernel that follows (its previous user has completed)
-    if (zero_n > 0 && blockIdx.x == 0 && (int)threadIdx.x < zero_n) zero[threadIdx.x] = 0u;
+    // (grid-stride: the layer-kernel path resets every counter of the step here)
+    for (int i = blockIdx.x * THREADS + threadIdx.x; i < zero_n; i += gridDim.x * THREADS) zero[i] = 0u;
     float4 v[MAXV];
     float ss = 0.f;
 #pragma unroll

@@ -83,6 +83,9 @@ struct Request {
     bool done = false;
     double t_submit = 0, t_first = 0, t_done = 0;
     int slot = -1;
+    uint64_t tag = 0;          // opaque caller value handed to the done hook (the gateway's request id)
+    bool cancel = false;       // rr_engine_cancel: the worker drops the row at the next step
+    bool detached = false;     // nobody will call rr_engine_wait: the worker frees the request when it finishes
 };
 
 }  // namespace rr
@@ -127,9 +130,12 @@ struct rr_engine {
                                       // GEMM's epilogue applies 1 / rms (RopeEpi)
     float* p_rowss = nullptr;         // [Tmax][pf_parts]
     int pf_parts = 0;
-    bool use_chain = false;           // persistent chain kernel between attention kernels (rr_chain.cu)
-    std::vector<ChainArgs> chain;     // per layer
-    unsigned* chain_counters = nullptr;   // [n_layers][8], zeroed at the start of every step
+    bool use_layer = false;           // decode: one persistent dataflow launch per layer between attention kernels (rr_layer.cu)
+    std::vector<LayerPlan> layer;     // [0] = QKV projection of layer 0 only; [1 + l] = layer l (phase 3 = QKV of l + 1 / lm_head)
+    MlpItem* layer_items = nullptr;   // device copies of the three schedules (first | mid | last)
+    unsigned* layer_ctr = nullptr;    // [(L + 1) * layer_ctr_words] dependency counters, zeroed by the first kernel of every step
+    int layer_ctr_words = 0;
+    float *rowss_a = nullptr, *rowss_b = nullptr;   // [Bm][ceil(hidden / 128)] partial sum(x^2) (deferred RMSNorm)
     bool fuse_silu = false;           // wgu interleaved + one gate/up plane: SiLU*mul lives in the GEMM epilogue
     bool fuse_mlp = false;            // decode: gate/up and down GEMMs in one persistent launch (gemm_mlp_tcgen05)
     std::vector<MlpPlan> mlp;         // per layer
@@ -167,8 +173,11 @@ struct rr_engine {
     uint64_t next_ticket = 1;
     std::chrono::steady_clock::time_point t0;
 
-    rr_engine_stats st;
+    rr_engine_stats st;                  // written under gpu_mu (launch / timing counters) or mu (queued, active_rows)
     uint64_t step_launches = 0;
+    // completion hook (the native gateway, rr_gateway.cu): called on the worker / submitting thread, outside `mu`
+    rr::EngineDoneHook hook = nullptr;
+    void* hook_ctx = nullptr;
 };
 
 static double now_s(rr_engine* e) {
@@ -201,7 +210,7 @@ static int pick_splits(int N, int K) {
     return s;
 }
 
-// One engine at a time per device.  The fused MLP kernel (and the experimental chain kernel) are persistent grids whose
+// One engine at a time per device.  The fused MLP kernel and the layer kernel (rr_layer.cu) are persistent grids whose
 // CTAs spin on work of sibling CTAs; two such grids interleaved on one GPU (two engines, two streams) could each hold
 // SMs the other's not-yet-resident CTAs need.  Every path below synchronises its stream before it releases this lock, so
 // engines that share a device alternate at prefill-chunk / decode-step granularity.  (The gateway creates one engine per
@@ -226,15 +235,16 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
     const rr_model_desc& d = e->d;
     const int B = e->Bm, L = d.n_layers;
     uint64_t nl = 0;
-    if (e->use_chain) {
-        // 3 + 2 L + 1 launches: embed, norm, QKV_0, then per layer attention + one persistent chain kernel
-        cudaMemsetAsync(e->chain_counters, 0, sizeof(unsigned) * 8 * L, s);
+    if (e->use_layer) {
+        // 3 + 2 L + 1 launches: embed, norm (deferred form: xn = bf16(x * gamma), sum(x^2); also zeroes every dependency
+        // counter of the step), QKV_0, then per layer attention + one persistent layer kernel (phase 3 of the last = lm_head)
         launch_embed(e->d_tok, (const __nv_bfloat16*)e->embed, e->x, B, d.hidden, e->d_slot, s); ++nl;
-        launch_add_rmsnorm(e->x, part_none(), (const __nv_bfloat16*)e->norm_attn[0], e->xn, B, d.hidden, d.rms_eps, s); ++nl;
-        if (gemm_launch(e->pl_qkv[0], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        launch_add_rmsnorm(e->x, part_none(), (const __nv_bfloat16*)e->norm_attn[0], e->xn, B, d.hidden, d.rms_eps, s,
+                           e->layer_ctr, (L + 1) * e->layer_ctr_words, e->rowss_b, (d.hidden + 127) / 128); ++nl;
+        if (layer_launch(e->layer[0], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         for (int l = 0; l < L; ++l) {
             launch_decode_attn(e->attn_args[l], s); nl += e->kv_splits > 1 ? 2 : 1;
-            if (launch_decode_chain(e->chain[l], e->bn_dec, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+            if (layer_launch(e->layer[1 + l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         }
         launch_argmax(part_f32(e->logits, 1, B, d.vocab), B, d.vocab, e->d_tok, nullptr, e->d_slot, e->d_pos, s); ++nl;
         if (n_launch) *n_launch = nl;
@@ -355,7 +365,6 @@ static int get_pf_plans(rr_engine* e, int T, rr_engine::PfPlans** out) {
             r.xhat = e->pxn; r.rowss_out = e->p_rowss; r.n_part_out = e->pf_parts;
         }
     }
-    if (e->pf_plans.size() > 64) e->pf_plans.clear();
     auto ins = e->pf_plans.emplace(T, std::move(P));
     *out = &ins.first->second;
     return RR_OK;
@@ -390,9 +399,12 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
     int32_t *p_ids = e->p_ids, *p_pos = p_ids + T, *p_slt = p_ids + 2 * T, *p_ss = p_ids + 3 * T,
             *p_sl = p_ss + n_seqs + 1, *p_last = p_sl + n_seqs;
 
+    // One set of plans (4 L TMA descriptors) built for Tmax rows; the live row count is a launch argument: TMA reads of
+    // rows >= T stay inside the Tmax-row buffers and every store is guarded by rowsA.
     rr_engine::PfPlans* P = nullptr;
-    int rc = get_pf_plans(e, T, &P);
+    int rc = get_pf_plans(e, e->Tmax, &P);
     if (rc != RR_OK) return rc;
+    auto launch_rows = [&](const GemmPlan& pl) { GemmPlan q = pl; q.rowsA = T; return gemm_launch(q, s); };
     uint64_t nl = 0;
     launch_embed(p_ids, (const __nv_bfloat16*)e->embed, e->px, T, d.hidden, nullptr, s); ++nl;
     if (e->defer_norm_pf)       // layer 0's operand in the deferred form: bf16(x * gamma), sum(x^2) in partial 0
@@ -407,7 +419,7 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         if (e->fuse_rope_pf) {
             P->qkv[l].rope.slot = p_slt; P->qkv[l].rope.pos = p_pos;
         }
-        if (gemm_launch(P->qkv[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        if (launch_rows(P->qkv[l]) != RR_OK) return RR_CUDA_ERROR; ++nl;
         RopeArgs ra;
         ra.qkv = part_bf16(e->pqkv, e->nqkv);
         ra.q_out = e->pq; ra.k_cache = kc; ra.v_cache = vc; ra.slot = p_slt; ra.pos = p_pos; ra.rows = T;
@@ -434,14 +446,14 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
                                n_seqs, d.hidden, d.rms_eps, s); ++nl;
             break;
         }
-        if (gemm_launch(P->o[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        if (launch_rows(P->o[l]) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->defer_norm_pf) {
             launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)e->norm_mlp[l], e->pxn, T,
                                d.hidden, d.rms_eps, s); ++nl;
         }
-        if (gemm_launch(P->gu[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        if (launch_rows(P->gu[l]) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->fuse_silu) { launch_silu_mul(part_bf16(e->pgu, 2 * d.inter), e->pact, T, d.inter, s); ++nl; }
-        if (gemm_launch(P->down[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
+        if (launch_rows(P->down[l]) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (!e->defer_norm_pf) {
             launch_add_rmsnorm(e->px, part_none(), (const __nv_bfloat16*)e->norm_attn[l + 1], e->pxn, T, d.hidden,
                                d.rms_eps, s); ++nl;
@@ -472,23 +484,45 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
 }
 
 // ---------------------------------------------------------------- worker (continuous batching)
-static void finish_request(rr_engine* e, Request* r, int status) {
+struct DoneNote { uint64_t tag, ticket; int status, n_gen; };
+
+// Caller holds e->mu.  Returns the hook call to make once the lock is released (tag == 0 and no hook: nothing).
+static void finish_request(rr_engine* e, Request* r, int status, std::vector<DoneNote>* notes = nullptr) {
     r->status = status;
     r->t_done = now_s(e);
     r->done = true;
+    if (notes && e->hook) notes->push_back(DoneNote{r->tag, r->ticket, status, (int)r->out.size()});
+    if (r->detached) {                   // cancelled by its owner: nobody waits for it
+        e->table.erase(r->ticket);
+        delete r;
+    }
+}
+static void run_hooks(rr_engine* e, std::vector<DoneNote>& notes) {
+    for (const DoneNote& n : notes) e->hook(e->hook_ctx, n.tag, n.ticket, n.status, n.n_gen);
+    notes.clear();
 }
 
 static void worker_main(rr_engine* e) {
     cudaSetDevice(e->o.device);
     std::vector<int32_t> ids, seq_start, slots;
     std::vector<Request*> chunk;
+    std::vector<DoneNote> notes;
     while (!e->stop.load()) {
+        run_hooks(e, notes);
         // ---- admit waiting requests into free rows (prefill has priority: best TTFT)
         chunk.clear(); ids.clear(); seq_start.assign(1, 0); slots.clear();
         int active = 0;
         {
             std::unique_lock<std::mutex> lk(e->mu);
-            for (int b = 0; b < e->Bm; ++b) active += e->row_req[b] != nullptr;
+            for (int b = 0; b < e->Bm; ++b) {
+                Request* r = e->row_req[b];
+                if (r && r->cancel) {                      // rr_engine_cancel: free the row, keep what was generated
+                    e->row_req[b] = nullptr; e->h_slot_mirror[b] = -1; e->slots_dirty = true;
+                    finish_request(e, r, RR_CANCELLED, &notes);
+                    continue;
+                }
+                active += r != nullptr;
+            }
             if (e->waiting.empty() && active == 0) {
                 e->cv_work.wait_for(lk, std::chrono::milliseconds(50));
                 continue;
@@ -522,7 +556,7 @@ static void worker_main(rr_engine* e) {
                 if (rc != RR_OK) {
                     e->row_req[r->slot] = nullptr;
                     e->h_slot_mirror[r->slot] = -1; e->slots_dirty = true;
-                    finish_request(e, r, RR_INTERNAL);
+                    finish_request(e, r, RR_INTERNAL, &notes);
                     continue;
                 }
                 r->t_first = t;
@@ -531,7 +565,7 @@ static void worker_main(rr_engine* e) {
                 if ((int)r->out.size() >= r->max_new) {
                     e->row_req[r->slot] = nullptr;
                     e->h_slot_mirror[r->slot] = -1; e->slots_dirty = true;
-                    finish_request(e, r, RR_OK);
+                    finish_request(e, r, RR_OK, &notes);
                 }
             }
             e->cv_done.notify_all();
@@ -564,19 +598,20 @@ static void worker_main(rr_engine* e) {
                 if (!r) continue;
                 if (rc != RR_OK) {
                     e->row_req[b] = nullptr; e->h_slot_mirror[b] = -1; e->slots_dirty = true;
-                    finish_request(e, r, RR_INTERNAL);
+                    finish_request(e, r, RR_INTERNAL, &notes);
                     continue;
                 }
                 r->out.push_back(e->h_tok[b]);
                 e->st.generated_tokens += 1;
                 if ((int)r->out.size() >= r->max_new) {
                     e->row_req[b] = nullptr; e->h_slot_mirror[b] = -1; e->slots_dirty = true;
-                    finish_request(e, r, RR_OK);
+                    finish_request(e, r, RR_OK, &notes);
                 }
             }
         }
         e->cv_done.notify_all();
     }
+    run_hooks(e, notes);
 }
 
 // ---------------------------------------------------------------- C-ABI
@@ -590,6 +625,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         return RR_INVALID_ARGUMENT;
     const int G = d.n_heads / d.n_kv_heads;
     if (!(G == 1 || G == 2 || G == 4 || G == 8)) return RR_INVALID_ARGUMENT;
+    if (d.hidden > 8192) return RR_INVALID_ARGUMENT;      // add_rmsnorm_kernel keeps one row in registers (rr_elementwise.cu)
     if (opts->max_batch < 1 || opts->max_batch > 256 || opts->ctx_max < 64 || opts->ctx_max % 64)
         return RR_INVALID_ARGUMENT;
     CK(cudaSetDevice(opts->device));
@@ -720,31 +756,63 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     // with the earlier row-per-thread epilogue the same fusion LOST 1.4 % (o-proj +35 %).
     e->defer_norm_pf = opts->reserved[3] == 0 && !getenv("RR_NO_DEFER_NORM") && d.hidden % 8 == 0 && e->pf_parts <= 64;
     if (e->defer_norm_pf) TRY(dalloc(e, &e->p_rowss, (size_t)e->Tmax * e->pf_parts));
-    e->use_chain = e->fuse_silu && opts->reserved[0] == 0 && e->bn_dec >= 32;
-    if (e->use_chain) {
-        TRY(dalloc(e, &e->chain_counters, (size_t)8 * L));
-        e->chain.resize(L);
-        for (int l = 0; l < L; ++l) {
-            ChainArgs& c = e->chain[l];
-            memset(&c, 0, sizeof(c));
-            TRY(chain_gemm_init(&c.g[0], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->part_o, d.hidden, e->s_o,
-                                OUT_TRANSPOSED_F32, e->bn_dec));
-            TRY(chain_gemm_init(&c.g[1], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, e->act, d.inter, 1,
-                                OUT_TRANSPOSED_SILU, e->bn_dec));
-            TRY(chain_gemm_init(&c.g[2], e->wdown[l], d.hidden, d.inter, e->act, B, e->part_down, d.hidden, e->s_down,
-                                OUT_TRANSPOSED_F32, e->bn_dec));
-            if (l + 1 < L)
-                TRY(chain_gemm_init(&c.g[3], e->wqkv[l + 1], e->nqkv, d.hidden, e->xn, B, e->part_qkv, e->nqkv, e->s_qkv,
-                                    OUT_TRANSPOSED_F32, e->bn_dec));
-            else
-                TRY(chain_gemm_init(&c.g[3], e->lm_head, d.vocab, d.hidden, e->xn, B, e->logits, d.vocab, 1,
-                                    OUT_TRANSPOSED_F32, e->bn_dec));
-            c.n[0].part = e->part_o; c.n[0].n_splits = e->s_o; c.n[0].split_stride = (long long)B * d.hidden;
-            c.n[0].w = (const __nv_bfloat16*)e->norm_mlp[l];
-            c.n[1].part = e->part_down; c.n[1].n_splits = e->s_down; c.n[1].split_stride = (long long)B * d.hidden;
-            c.n[1].w = (const __nv_bfloat16*)((l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm);
-            c.x = e->x; c.xn = e->xn; c.rows = B; c.hidden = d.hidden; c.eps = d.rms_eps;
-            c.counters = e->chain_counters + 8 * l;
+    // ---- persistent layer kernel (default when the fused MLP is possible; reserved[0] = 1 / RR_NO_LAYER_FUSE=1: off)
+    e->use_layer = e->fuse_mlp && opts->reserved[0] == 0 && !getenv("RR_NO_LAYER_FUSE");
+    if (e->use_layer) {
+        const int grid = num_sms();
+        const int tiles_h = (d.hidden + 127) / 128, kb_o = (e->nq + 63) / 64;
+        int s_o = grid / tiles_h;                         // one O item per CTA (their epilogues wait for each other)
+        if (s_o > 8) s_o = 8;
+        while (s_o > 1 && kb_o / s_o < 4) --s_o;
+        if (s_o > e->s_o) s_o = e->s_o > 0 ? e->s_o : 1;  // part_o holds e->s_o planes
+        if (s_o < 1 || tiles_h * s_o > grid) e->use_layer = false;
+        if (e->use_layer) {
+            LayerShape sh[3];
+            for (int k = 0; k < 3; ++k) {
+                sh[k].hidden = d.hidden; sh[k].inter = d.inter; sh[k].nq = e->nq; sh[k].s_o = s_o;
+                sh[k].slice_kb = e->mlp_slice_kb; sh[k].has_main = k > 0;
+                sh[k].rowsA3 = k < 2 ? e->nqkv : d.vocab; sh[k].s3 = k < 2 ? e->s_qkv : 1;
+            }
+            std::vector<MlpItem> sched[3];
+            int mx[3];
+            size_t total = 0;
+            for (int k = 0; k < 3; ++k) {
+                mx[k] = layer_schedule(grid, sh[k], &sched[k]);
+                if (mx[k] < 0) { e->use_layer = false; break; }
+                total += sched[k].size();
+            }
+            if (e->use_layer) {
+                TRY(dalloc(e, &e->layer_items, total));
+                size_t off[3], o = 0;
+                for (int k = 0; k < 3; ++k) {
+                    off[k] = o;
+                    TRYC(cudaMemcpy(e->layer_items + o, sched[k].data(), sched[k].size() * sizeof(MlpItem), cudaMemcpyHostToDevice));
+                    o += sched[k].size();
+                }
+                e->layer_ctr_words = (layer_counter_words(sh[1]) + 31) & ~31;
+                TRY(dalloc(e, &e->layer_ctr, (size_t)(L + 1) * e->layer_ctr_words));
+                TRY(dalloc(e, &e->rowss_a, (size_t)B * tiles_h));
+                TRY(dalloc(e, &e->rowss_b, (size_t)B * tiles_h));
+                e->layer.resize(L + 1);
+                for (int i = 0; i <= L; ++i) {
+                    const int l = i - 1;                  // -1: the QKV projection of layer 0 alone
+                    const int k = i == 0 ? 0 : (l + 1 < L ? 1 : 2);
+                    LayerBuffers bf;
+                    memset(&bf, 0, sizeof(bf));
+                    bf.x = e->x; bf.xhat = e->xn; bf.rowss_a = e->rowss_a; bf.rowss_b = e->rowss_b; bf.rows = B; bf.ld_rows = B;
+                    bf.eps = d.rms_eps;
+                    bf.l2_ahead = getenv("RR_LAYER_L2_AHEAD") ? atoi(getenv("RR_LAYER_L2_AHEAD")) : 0;
+                    if (l >= 0) {
+                        bf.wo = e->wo[l]; bf.wgu = e->wgu[l]; bf.wdown = e->wdown[l]; bf.attn_out = e->attn_out; bf.act = e->act;
+                        bf.part_o = e->part_o; bf.part_d = e->part_down; bf.gamma_a = (const __nv_bfloat16*)e->norm_mlp[l];
+                        bf.gamma_b = (const __nv_bfloat16*)(l + 1 < L ? e->norm_attn[l + 1] : e->final_norm);
+                    }
+                    if (k < 2) { bf.w3 = e->wqkv[l + 1]; bf.out3 = e->part_qkv; bf.ldo3 = e->nqkv; }
+                    else { bf.w3 = e->lm_head; bf.out3 = e->logits; bf.ldo3 = d.vocab; }
+                    TRY(layer_plan_init(&e->layer[i], sh[k], bf, e->bn_dec, e->layer_items + off[k], mx[k], grid,
+                                        e->layer_ctr + (size_t)i * e->layer_ctr_words));
+                }
+            }
         }
     }
     if (e->fuse_mlp) {
@@ -853,8 +921,9 @@ static bool injected_failure(const rr_engine* e, uint64_t ticket) {
     return (double)(z >> 11) * (1.0 / 9007199254740992.0) < (double)e->o.fail_prob;
 }
 
-RR_API int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int max_new_tokens,
-                            uint64_t* ticket) {
+namespace rr {
+int engine_submit_tagged(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int max_new_tokens, uint64_t tag,
+                         uint64_t* ticket) {
     if (!e || !prompt_ids || !ticket || n_prompt < 1 || max_new_tokens < 1) return RR_INVALID_ARGUMENT;
     if (n_prompt + max_new_tokens > e->o.ctx_max || n_prompt > e->Tmax) return RR_INVALID_ARGUMENT;
     for (int i = 0; i < n_prompt; ++i)
@@ -864,21 +933,69 @@ RR_API int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_promp
     r->prompt.assign(prompt_ids, prompt_ids + n_prompt);
     r->max_new = max_new_tokens;
     r->out.reserve(max_new_tokens);
+    r->tag = tag;
+    std::vector<DoneNote> notes;
     {
         std::lock_guard<std::mutex> lk(e->mu);
         r->ticket = e->next_ticket++;
         r->t_submit = now_s(e);
         e->table[r->ticket] = r;
+        *ticket = r->ticket;
         if (injected_failure(e, r->ticket)) {
             r->t_first = r->t_submit;
-            finish_request(e, r, RR_BACKEND_FAILED);
+            finish_request(e, r, RR_BACKEND_FAILED, &notes);
         } else {
             e->waiting.push_back(r);
         }
-        *ticket = r->ticket;
     }
     e->cv_work.notify_one();
     e->cv_done.notify_all();
+    run_hooks(e, notes);
+    return RR_OK;
+}
+void engine_set_done_hook(rr_engine* e, EngineDoneHook fn, void* ctx) {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->hook = fn; e->hook_ctx = ctx;
+}
+int engine_limits(const rr_engine* e, int* ctx_max, int* max_prefill, int* vocab) {
+    if (!e) return RR_INVALID_ARGUMENT;
+    if (ctx_max) *ctx_max = e->o.ctx_max;
+    if (max_prefill) *max_prefill = e->Tmax;
+    if (vocab) *vocab = e->d.vocab;
+    return RR_OK;
+}
+}  // namespace rr
+
+RR_API int rr_engine_submit(rr_engine* e, const int32_t* prompt_ids, int n_prompt, int max_new_tokens,
+                            uint64_t* ticket) {
+    return rr::engine_submit_tagged(e, prompt_ids, n_prompt, max_new_tokens, 0, ticket);
+}
+
+// Abandon a request (client gone / timed out): a queued request is dropped, a running one gives up its decode row at the
+// next step; a finished one is just freed.  The ticket is consumed: do not wait on it afterwards.
+RR_API int rr_engine_cancel(rr_engine* e, uint64_t ticket) {
+    if (!e) return RR_INVALID_ARGUMENT;
+    std::vector<DoneNote> notes;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        auto it = e->table.find(ticket);
+        if (it == e->table.end()) return RR_INVALID_ARGUMENT;
+        Request* r = it->second;
+        if (r->done) {
+            e->table.erase(it);
+            delete r;
+        } else {
+            r->detached = true;
+            bool queued = false;
+            for (auto q = e->waiting.begin(); q != e->waiting.end(); ++q)
+                if (*q == r) { e->waiting.erase(q); queued = true; break; }
+            if (queued) finish_request(e, r, RR_CANCELLED, &notes);      // frees it (detached)
+            else r->cancel = true;                                       // active row: the worker drops it
+        }
+    }
+    e->cv_work.notify_one();
+    e->cv_done.notify_all();
+    run_hooks(e, notes);
     return RR_OK;
 }
 
@@ -888,13 +1005,21 @@ RR_API int rr_engine_peek(rr_engine* e, uint64_t ticket, int have, double timeou
                           int max_tokens_out, int32_t* n_generated, int32_t* done, double* t_first_token_s) {
     if (!e || !n_generated || !done) return RR_INVALID_ARGUMENT;
     std::unique_lock<std::mutex> lk(e->mu);
-    auto it = e->table.find(ticket);
-    if (it == e->table.end()) return RR_INVALID_ARGUMENT;
-    Request* r = it->second;
     const auto deadline = std::chrono::steady_clock::now() +
                           std::chrono::duration<double>(timeout_s > 0 ? timeout_s : 1e9);
-    while (!r->done && (int)r->out.size() <= have) {
-        if (e->cv_done.wait_until(lk, deadline) == std::cv_status::timeout) break;
+    Request* r = nullptr;
+    for (;;) {
+        // looked up again after every wake-up: another thread may have consumed (wait) or cancelled the ticket meanwhile
+        auto it = e->table.find(ticket);
+        if (it == e->table.end()) return RR_INVALID_ARGUMENT;
+        r = it->second;
+        if (r->done || (int)r->out.size() > have) break;
+        if (e->cv_done.wait_until(lk, deadline) == std::cv_status::timeout) {
+            it = e->table.find(ticket);
+            if (it == e->table.end()) return RR_INVALID_ARGUMENT;
+            r = it->second;
+            break;
+        }
     }
     const int n = (int)r->out.size();
     *n_generated = n;
@@ -911,15 +1036,20 @@ RR_API int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_co
                           int max_tokens_out) {
     if (!e || !out) return RR_INVALID_ARGUMENT;
     std::unique_lock<std::mutex> lk(e->mu);
-    auto it = e->table.find(ticket);
-    if (it == e->table.end()) return RR_INVALID_ARGUMENT;
-    Request* r = it->second;
     const auto deadline = std::chrono::steady_clock::now() +
                           std::chrono::duration<double>(timeout_s > 0 ? timeout_s : 1e9);
-    while (!r->done) {
-        if (e->cv_done.wait_until(lk, deadline) == std::cv_status::timeout && !r->done) {
+    Request* r = nullptr;
+    for (;;) {
+        auto it = e->table.find(ticket);
+        if (it == e->table.end()) return RR_INVALID_ARGUMENT;      // unknown, already consumed, or cancelled
+        r = it->second;
+        if (r->done) break;
+        if (e->cv_done.wait_until(lk, deadline) == std::cv_status::timeout) {
+            it = e->table.find(ticket);
+            if (it == e->table.end()) return RR_INVALID_ARGUMENT;
+            if (it->second->done) { r = it->second; break; }
             out->ticket = ticket; out->status = RR_TIMEOUT;
-            return RR_TIMEOUT;   // the request stays in flight; wait again or let it finish
+            return RR_TIMEOUT;   // the request stays in flight: wait again, or rr_engine_cancel
         }
     }
     out->ticket = ticket; out->status = r->status; out->n_prompt = (int)r->prompt.size();
@@ -930,7 +1060,7 @@ RR_API int rr_engine_wait(rr_engine* e, uint64_t ticket, double timeout_s, rr_co
         memcpy(tokens_out, r->out.data(), sizeof(int32_t) * n);
     }
     const int status = r->status;
-    e->table.erase(it);
+    e->table.erase(ticket);
     delete r;
     return status == RR_OK ? RR_OK : status;
 }
@@ -957,6 +1087,7 @@ RR_API double rr_engine_now(rr_engine* e) { return e ? now_s(e) : 0.0; }
 
 RR_API int rr_engine_get_stats(rr_engine* e, rr_engine_stats* out) {
     if (!e || !out) return RR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> gl(e->gpu_mu);      // the worker updates the counters while it holds gpu_mu (then mu)
     std::lock_guard<std::mutex> lk(e->mu);
     *out = e->st;
     return RR_OK;
@@ -964,6 +1095,7 @@ RR_API int rr_engine_get_stats(rr_engine* e, rr_engine_stats* out) {
 
 RR_API int rr_engine_reset_stats(rr_engine* e) {
     if (!e) return RR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> gl(e->gpu_mu);
     std::lock_guard<std::mutex> lk(e->mu);
     memset(&e->st, 0, sizeof(e->st));
     return RR_OK;

@@ -1,5 +1,5 @@
 // rr_gemm_dev.cuh — device-side pieces shared by the tcgen05 GEMM kernel (rr_gemm.cu) and the persistent
-// decode chain kernel (rr_chain.cu): tile configuration, the per-CTA work schedule, small helpers.
+// decode layer kernel (rr_layer.cu): tile configuration, the per-CTA work schedule, small helpers.
 #pragma once
 #include "rr_ptx.cuh"
 #include "rr_launch.cuh"

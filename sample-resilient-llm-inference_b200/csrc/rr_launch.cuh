@@ -21,7 +21,8 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 static __device__ unsigned long long* rr_trace_ptr = nullptr;
 static inline void rr_trace_set_local(unsigned long long* p) { cudaMemcpyToSymbol(rr_trace_ptr, &p, sizeof(p)); }
 enum TraceId { TR_GEMM_DEC = 1, TR_GEMM_PF = 2, TR_ATTN_DEC = 3, TR_ATTN_PF = 4, TR_NORM = 5, TR_ROPE = 6,
-               TR_SILU = 7, TR_EMBED = 8, TR_ARGMAX = 9, TR_COMBINE = 10, TR_MISC = 11 };
+               TR_SILU = 7, TR_EMBED = 8, TR_ARGMAX = 9, TR_COMBINE = 10, TR_MISC = 11,
+               TR_LAYER_PH0 = 12 };  // + k: sample CTAs of the layer kernel finished an item (0 O, 1 gate/up, 2 down, 3 reduce, 4 next)
 __device__ __forceinline__ unsigned long long rr_gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -48,6 +49,16 @@ __device__ __forceinline__ void trace_mark(int kid) {
     if (slot >= (int)p[1]) return;
     const unsigned long long t = rr_gtimer();
     p[2 + 4 * slot] = (unsigned long long)kid;
+    p[3 + 4 * slot] = t; p[4 + 4 * slot] = t; p[5 + 4 * slot] = t;
+}
+// marker from a few sample CTAs (0, 37, 74, 111, ...): kid in the low byte, CTA index above it
+__device__ __forceinline__ void trace_mark_cta(int kid) {
+    unsigned long long* p = rr_trace_ptr;
+    if (p == nullptr || blockIdx.x % 37 != 0) return;
+    const int slot = (int)atomicAdd(p, 1ull);
+    if (slot >= (int)p[1]) return;
+    const unsigned long long t = rr_gtimer();
+    p[2 + 4 * slot] = (unsigned long long)(kid | ((int)blockIdx.x << 8));
     p[3 + 4 * slot] = t; p[4 + 4 * slot] = t; p[5 + 4 * slot] = t;
 }
 __device__ __forceinline__ void trace_end(int slot) {

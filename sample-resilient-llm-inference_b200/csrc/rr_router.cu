@@ -16,6 +16,7 @@
 // doubles, _randbelow = getrandbits rejection loop (Lib/random.py:242-250, 454-489).
 // Latency/atomic-bound: not a roofline kernel; reported as ns/event.
 #include "rr_kernels.h"
+#include "rr_launch.cuh"
 
 #include <mutex>
 #include <new>
@@ -464,6 +465,7 @@ struct rr_router {
     int smem_bytes;         // > 0: router_kernel_smem is usable (state fits in one CTA's shared memory)
     cudaEvent_t last;       // completion of the latest launch: launches on one router are serialised across streams
     std::mutex mu;
+    std::vector<int32_t> replica;   // per deployment: engine / GPU that serves it (rr_deployment_desc.replica)
 };
 
 #define CK(x)                                   \
@@ -523,6 +525,7 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
     if (!r) return RR_INTERNAL;
     memset(&r->dev, 0, sizeof(r->dev));
     r->device = device; r->n_deps = n_deps; r->n_groups = n_groups;
+    for (int i = 0; i < n_deps; ++i) r->replica.push_back(deps[i].replica);
     r->h_events = nullptr; r->h_dec = nullptr; r->d_events = nullptr; r->d_dec = nullptr; r->cap = 0;
 
     // arena layout (8-byte aligned pieces first)
@@ -582,8 +585,11 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
     r->smem_bytes = 0;
     {
         const RouterSmemLayout L = router_smem_layout(n_deps, n_groups, n_fb);
+        // The attribute is per function AND per device: raise it once per device to the cap every router may need (a later,
+        // smaller router must not lower it under an earlier one); a launch then only states its own size.
+        static std::atomic<uint64_t> attr_set{0};
         if (L.total <= 200 * 1024 && !getenv("RR_ROUTER_GLOBAL_STATE") &&
-            cudaFuncSetAttribute(router_kernel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess)
+            rr::ensure_dyn_smem(router_kernel_smem, 200 * 1024, attr_set) == cudaSuccess)
             r->smem_bytes = (int)L.total;
     }
     int rc = ensure_cap(r, 1024);
@@ -591,6 +597,18 @@ RR_API int rr_router_create(const rr_deployment_desc* deps, int n_deps, int n_gr
     *out = r;
     return RR_OK;
 }
+
+namespace rr {
+int router_shape(const rr_router* r, int* n_deployments, int* n_groups) {
+    if (!r) return RR_INVALID_ARGUMENT;
+    if (n_deployments) *n_deployments = r->n_deps;
+    if (n_groups) *n_groups = r->n_groups;
+    return RR_OK;
+}
+int router_dep_replica(const rr_router* r, int deployment) {
+    return (r && deployment >= 0 && deployment < r->n_deps) ? r->replica[deployment] : -1;
+}
+}  // namespace rr
 
 RR_API void rr_router_destroy(rr_router* r) {
     if (!r) return;

@@ -191,7 +191,12 @@ class Router:
             config = build_config(model_list or [], rs)
         self.cfg = config
         self.backends: Dict[int, Any] = dict(backends or {})
+        self._custom_clock = clock is not None
         self.clock = clock or time.time
+        self._gw = None                 # rr_gateway handle (native per-request path), created on first use
+        self._gw_sig = None
+        self._gw_lock = threading.Lock()
+        self.record_trace = 0           # > 0: the gateway keeps the last N (event, decision) pairs (gateway_trace())
         self.default_max_tokens = default_max_tokens
         deps = config.deployments
         if not deps:
@@ -216,9 +221,165 @@ class Router:
         return cls(config=load_config(path), **kw)
 
     def close(self):
+        if getattr(self, "_gw", None):
+            _lib.lib.rr_gateway_destroy(self._gw)
+            self._gw = None
         if getattr(self, "_h", None):
             _lib.lib.rr_router_destroy(self._h)
             self._h = None
+
+    # ---- native per-request path (rr_gateway.cu) ------------------------------------------------------
+    def _gateway(self):
+        """rr_gateway over this router and its engines, or None when a backend is not a native engine (StubBackend:
+        BASELINE config #1, plumbing only -- the host loop below serves those)."""
+        if not self.backends or not all(isinstance(b, EngineBackend) for b in self.backends.values()):
+            return None
+        sig = tuple(sorted((k, id(b.engine)) for k, b in self.backends.items()))
+        with self._gw_lock:
+            if self._gw is not None and self._gw_sig == sig:
+                return self._gw
+            if self._gw is not None:
+                _lib.lib.rr_gateway_destroy(self._gw)
+                self._gw = None
+            keys = sorted(self.backends)
+            engs = (C.c_void_p * len(keys))(*[self.backends[k].engine._h for k in keys])
+            reps = (C.c_int32 * len(keys))(*keys)
+            opts = _lib.GatewayOpts(1 if self._custom_clock else 0, int(self.record_trace), 0)
+            h = C.c_void_p()
+            _lib.check(_lib.lib.rr_gateway_create(self._h, engs, reps, len(keys), C.byref(opts), C.byref(h)),
+                       "rr_gateway_create")
+            self._gw, self._gw_sig = h, sig
+            return h
+
+    def gateway_stats(self) -> dict:
+        gw = self._gateway()
+        if gw is None:
+            return {}
+        s = _lib.GatewayStats()
+        _lib.check(_lib.lib.rr_gateway_get_stats(gw, C.byref(s)), "rr_gateway_get_stats")
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def gateway_trace(self) -> List[Tuple[Tuple[int, int, int, int, int], Tuple[int, int, int, int]]]:
+        """[(event, decision)] recorded by the gateway (record_trace > 0), oldest first: the serialised trace K1 processed."""
+        gw = self._gateway()
+        n = C.c_int32()
+        if gw is None or _lib.lib.rr_gateway_trace(gw, None, None, 0, C.byref(n)) not in (0, 4) or n.value == 0:
+            return []
+        ev, dec = (_lib.Event * n.value)(), (_lib.Decision * n.value)()
+        _lib.check(_lib.lib.rr_gateway_trace(gw, ev, dec, n.value, C.byref(n)), "rr_gateway_trace")
+        return [((e.type, e.target, e.tokens, e.chain_start, e.now_ms), (d.status, d.deployment, d.served_group, d.chain_pos))
+                for e, d in zip(ev[: n.value], dec[: n.value])]
+
+    def _gw_response(self, res, toks, n_prompt, t_start, detok=True) -> ModelResponse:
+        d = self.cfg.deployments[res.deployment]
+        toks = [int(t) for t in toks[: res.n_generated]]
+        return ModelResponse(
+            id="chatcmpl-" + uuid.uuid4().hex[:24], model=d.response_model,
+            choices=[Choice(0, Message("assistant", detokenize(toks) if detok else ""))],
+            usage=Usage(n_prompt, len(toks), n_prompt + len(toks)), created=int(time.time()),
+            _token_ids=toks, _deployment=res.deployment, _model_group=self.cfg.groups[res.served_group],
+            _fell_back=res.chain_pos > 0, _ttft_s=res.t_first_token_s - res.t_submit_s,
+            _latency_s=time.perf_counter() - t_start)
+
+    def _gw_error(self, status: int, model: str, res=None, timeout=None) -> APIError:
+        if status == 1:
+            return RateLimitError(f"No deployments available for selected model, passed model={model} (rate limited)")
+        if status == 2:
+            return BadRequestError(f"Invalid model name passed in model={model}")
+        if status == 4:
+            return BadRequestError("prompt + max_tokens exceed the context window of the deployment, or a token id is "
+                                   "outside its vocabulary")
+        if status == 6:
+            return APITimeoutError(f"Request timed out after {timeout}s")
+        if status == 7:
+            dep = res.deployment if res is not None else -1
+            return APIError(f"backend failure on deployment {dep} and no fallback available for model={model}")
+        return APIError(f"{_lib.lib.rr_strerror(status).decode()} (model={model})")
+
+    def _gw_submit(self, gw, g: int, prompt_ids, max_new: int, model: str) -> int:
+        ids = np.ascontiguousarray(np.asarray(prompt_ids, dtype=np.int32))
+        if self._custom_clock:
+            _lib.lib.rr_gateway_set_now(gw, self.now_ms())
+        t = C.c_uint64()
+        rc = _lib.lib.rr_gateway_submit(gw, g, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids), max_new, C.byref(t))
+        if rc != 0:
+            raise self._gw_error(rc, model)
+        return t.value
+
+    def _completion_gw(self, gw, model, g, prompt_ids, max_new, timeout):
+        t_start = time.perf_counter()
+        ticket = self._gw_submit(gw, g, prompt_ids, max_new, model)
+        res = _lib.GatewayResult()
+        toks = np.zeros(max_new, dtype=np.int32)
+        rc = _lib.lib.rr_gateway_wait(gw, ticket, float(timeout or 0.0), C.byref(res),
+                                      toks.ctypes.data_as(C.POINTER(C.c_int32)), max_new)
+        if rc == 6:                      # client-side timeout: give the row back, count a failure against the deployment
+            _lib.lib.rr_gateway_cancel(gw, ticket, 1)
+            raise self._gw_error(6, model, res, timeout)
+        if rc != 0:
+            raise self._gw_error(rc, model, res, timeout)
+        return self._gw_response(res, toks, len(prompt_ids), t_start)
+
+    def _stream_gw(self, gw, model, g, prompt_ids, max_new, timeout):
+        ticket = self._gw_submit(gw, g, prompt_ids, max_new, model)
+        deadline = None if not timeout else time.perf_counter() + timeout
+        res = _lib.GatewayResult()
+        toks = np.zeros(max_new, dtype=np.int32)
+        n, done = C.c_int32(), C.c_int32()
+        sent, finished = 0, False
+        try:
+            while True:
+                _lib.check(_lib.lib.rr_gateway_peek(gw, ticket, sent, 0.05, toks.ctypes.data_as(C.POINTER(C.c_int32)), max_new,
+                                                    C.byref(n), C.byref(done), C.byref(res)), "rr_gateway_peek")
+                if done.value:
+                    rc = _lib.lib.rr_gateway_wait(gw, ticket, 1.0, C.byref(res), toks.ctypes.data_as(C.POINTER(C.c_int32)), max_new)
+                    finished = True
+                    if rc != 0:
+                        raise self._gw_error(rc, model, res, timeout)
+                    label = self.cfg.deployments[res.deployment].response_model
+                    ttft = res.t_first_token_s - res.t_submit_s
+                    if res.n_generated > sent:
+                        yield label, [int(t) for t in toks[sent: res.n_generated]], False, ttft
+                    yield label, [], True, ttft
+                    return
+                if n.value > sent and res.deployment >= 0:
+                    label = self.cfg.deployments[res.deployment].response_model
+                    yield label, [int(t) for t in toks[sent: n.value]], False, 0.0
+                    sent = n.value
+                if deadline is not None and time.perf_counter() > deadline:
+                    _lib.lib.rr_gateway_cancel(gw, ticket, 1)
+                    finished = True
+                    raise self._gw_error(6, model, res, timeout)
+        finally:
+            if not finished:             # the consumer went away (SSE client disconnected): free the row, no failure counted
+                _lib.lib.rr_gateway_cancel(gw, ticket, 0)
+
+    def _batch_gw(self, gw, model, g, prompts, max_new, timeout):
+        t0 = time.perf_counter()
+        n = len(prompts)
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32) for p in prompts]))
+        start = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum([len(p) for p in prompts], out=start[1:])
+        if self._custom_clock:
+            _lib.lib.rr_gateway_set_now(gw, self.now_ms())
+        tk = (C.c_uint64 * n)()
+        rc = _lib.lib.rr_gateway_submit_batch(gw, g, ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              start.ctypes.data_as(C.POINTER(C.c_int32)), n, max_new,
+                                              1 if self.cfg.routing_strategy == "split" else 0, tk)
+        if rc != 0:
+            raise self._gw_error(rc, model)
+        out: List[Any] = [None] * n
+        toks = np.zeros(max_new, dtype=np.int32)
+        for i in range(n):
+            res = _lib.GatewayResult()
+            left = None if not timeout else max(0.001, timeout - (time.perf_counter() - t0))
+            rc = _lib.lib.rr_gateway_wait(gw, tk[i], float(left or 0.0), C.byref(res),
+                                          toks.ctypes.data_as(C.POINTER(C.c_int32)), max_new)
+            if rc == 6:
+                _lib.lib.rr_gateway_cancel(gw, tk[i], 1)
+            out[i] = self._gw_response(res, toks, len(prompts[i]), t0, detok=False) if rc == 0 \
+                else self._gw_error(rc, model, res, timeout)
+        return out
 
     def __del__(self):
         try:
@@ -235,6 +396,7 @@ class Router:
         n = len(events)
         if n == 0:
             return []
+        self._quiesce()
         ev = (_lib.Event * n)()
         for i, e in enumerate(events):
             ev[i] = _lib.Event(*e)
@@ -242,7 +404,13 @@ class Router:
         _lib.check(_lib.lib.rr_router_process(self._h, ev, n, out), "rr_router_process")
         return [(d.status, d.deployment, d.served_group, d.chain_pos) for d in out]
 
+    def _quiesce(self):
+        """Let the gateway's dispatcher post what is still queued (DONE / FAIL reports of finished requests)."""
+        if self._gw is not None:
+            _lib.lib.rr_gateway_quiesce(self._gw, 5.0)
+
     def snapshot(self) -> List[dict]:
+        self._quiesce()
         n = len(self.cfg.deployments)
         s = (_lib.DeploymentState * n)()
         _lib.check(_lib.lib.rr_router_snapshot(self._h, s), "rr_router_snapshot")
@@ -257,9 +425,8 @@ class Router:
         return b
 
     def _vocab(self) -> int:
-        for b in self.backends.values():
-            return b.vocab
-        return 128256
+        """Token ids must be valid on every replica a request may fall back to: the smallest vocabulary attached."""
+        return min((b.vocab for b in self.backends.values()), default=128256)
 
     def completion(self, model: str, messages: Optional[Sequence[dict]] = None, timeout: Optional[float] = None,
                    max_tokens: Optional[int] = None, prompt_ids: Optional[Sequence[int]] = None,
@@ -271,6 +438,10 @@ class Router:
             prompt_ids = tokenize(messages_to_text(messages or []), self._vocab())
         n_prompt = len(prompt_ids)
         max_new = max_tokens or self.default_max_tokens
+        gw = self._gateway()
+        if gw is not None:
+            return self._completion_gw(gw, model, g, prompt_ids, max_new, timeout)
+        # ---- host loop (StubBackend): same admission events, one K1 launch per event
         t_start = time.perf_counter()
         chain_start = 0
         last_err: Optional[APIError] = None
@@ -281,9 +452,13 @@ class Router:
                     f"No deployments available for selected model, passed model={model} (rate limited)")
             if status != 0:
                 raise BadRequestError(f"Invalid model name passed in model={model}")
-            backend = self._backend_for(dep)
             remaining = None if timeout is None else max(0.001, timeout - (time.perf_counter() - t_start))
-            st, toks, ttft, lat = backend.wait(backend.submit(prompt_ids, max_new), remaining)
+            try:
+                backend = self._backend_for(dep)
+                st, toks, ttft, lat = backend.wait(backend.submit(prompt_ids, max_new), remaining)
+            except Exception as exc:     # the request was admitted: never leave its in-flight slot behind
+                self.process([(EV_FAIL, dep, 0, 0, self.now_ms())])
+                raise exc if isinstance(exc, APIError) else APIError(f"backend error on deployment {dep}: {exc}")
             if st == 0:
                 self.process([(EV_DONE, dep, len(toks), 0, self.now_ms())])
                 d = self.cfg.deployments[dep]
@@ -311,6 +486,11 @@ class Router:
         if prompt_ids is None:
             prompt_ids = tokenize(messages_to_text(messages or []), self._vocab())
         max_new = max_tokens or self.default_max_tokens
+        gw = self._gateway()
+        if gw is not None:
+            yield from self._stream_gw(gw, model, g, prompt_ids, max_new, timeout)
+            return
+        deadline = None if not timeout else time.perf_counter() + timeout
         chain_start = 0
         while True:
             (status, dep, sg, pos), = self.process([(EV_ADMIT, g, len(prompt_ids), chain_start, self.now_ms())])
@@ -318,24 +498,30 @@ class Router:
                 raise RateLimitError(f"No deployments available for selected model, passed model={model} (rate limited)")
             if status != 0:
                 raise BadRequestError(f"Invalid model name passed in model={model}")
-            backend = self._backend_for(dep)
-            label = self.cfg.deployments[dep].response_model
-            h = backend.submit(prompt_ids, max_new)
-            sent, failed = 0, False
-            while True:
-                toks, done, ttft = backend.peek(h, sent)
-                if len(toks) > sent:
-                    yield label, toks[sent:], False, ttft
-                    sent = len(toks)
-                if done:
-                    st, toks, ttft, _lat = backend.wait(h, timeout)
-                    failed = st != 0
-                    break
-            if not failed:
-                self.process([(EV_DONE, dep, sent, 0, self.now_ms())])
-                yield label, [], True, ttft
-                return
-            self.process([(EV_FAIL, dep, 0, 0, self.now_ms())])
+            sent, failed, settled = 0, False, False
+            try:
+                backend = self._backend_for(dep)
+                label = self.cfg.deployments[dep].response_model
+                h = backend.submit(prompt_ids, max_new)
+                while True:
+                    toks, done, ttft = backend.peek(h, sent)
+                    if len(toks) > sent:
+                        yield label, toks[sent:], False, ttft
+                        sent = len(toks)
+                    if done:
+                        st, toks, ttft, _lat = backend.wait(h, timeout)
+                        failed = st != 0
+                        break
+                    if deadline is not None and time.perf_counter() > deadline:
+                        raise APITimeoutError(f"Request timed out after {timeout}s")
+                if not failed:
+                    self.process([(EV_DONE, dep, sent, 0, self.now_ms())])
+                    settled = True
+                    yield label, [], True, ttft
+                    return
+            finally:
+                if not settled:          # failure, timeout, or the consumer closed the generator: release the slot
+                    self.process([(EV_FAIL if failed or sent == 0 else EV_DONE, dep, sent, 0, self.now_ms())])
             if sent > 0:
                 raise APIError(f"backend failure on deployment {dep} after {sent} tokens")
             chain_start = pos + 1
@@ -348,6 +534,9 @@ class Router:
         g = self.cfg.group_index(model)
         if g < 0:
             raise BadRequestError(f"Invalid model name passed in model={model}")
+        gw = self._gateway()
+        if gw is not None:
+            return self._batch_gw(gw, model, g, prompts, max_tokens, timeout)
         now = self.now_ms()
         head = [(EV_BURST, g, len(prompts), 0, now)] if self.cfg.routing_strategy == "split" else []
         dec = self.process(head + [(EV_ADMIT, g, len(p), 0, now) for p in prompts])[len(head):]
@@ -358,8 +547,12 @@ class Router:
             if status != 0:
                 out[i] = RateLimitError(f"No deployments available for model={model} (rate limited)")
                 continue
-            b = self._backend_for(dep)
-            handles[i] = (b, b.submit(prompts[i], max_tokens))
+            try:
+                b = self._backend_for(dep)
+                handles[i] = (b, b.submit(prompts[i], max_tokens))
+            except Exception as exc:     # admitted but never started: release the slot, keep serving the others
+                self.process([(EV_FAIL, dep, 0, 0, self.now_ms())])
+                out[i] = exc if isinstance(exc, APIError) else APIError(f"backend error on deployment {dep}: {exc}")
         post = []
         retry = []
         for i, h in enumerate(handles):

@@ -31,6 +31,13 @@ def create_app(router: Router):
     app = FastAPI(title="rr_b200 gateway")
     t_start = time.time()
 
+    @app.on_event("startup")
+    async def _raise_thread_limit():
+        # every in-flight request parks one worker thread in rr_gateway_wait (GIL released); the default limit of 40 would
+        # cap the concurrency below one replica's 64 decode rows
+        import anyio.to_thread
+        anyio.to_thread.current_default_thread_limiter().total_tokens = 2048
+
     async def stream_completion(model, messages, body):
         """Server-sent events in the OpenAI chunk format; the first chunk leaves when the first token exists (TTFT)."""
         import json as _json
@@ -56,12 +63,15 @@ def create_app(router: Router):
                                                                         "finish_reason": "length" if done else None}]}) + "\n\n"
 
         def events():
-            label, toks, done, _ = first
-            yield chunk(label, toks, done)
-            if not done:
-                for label, toks, done, _ in gen:
-                    yield chunk(label, toks, done)
-            yield "data: [DONE]\n\n"
+            try:
+                label, toks, done, _ = first
+                yield chunk(label, toks, done)
+                if not done:
+                    for label, toks, done, _ in gen:
+                        yield chunk(label, toks, done)
+                yield "data: [DONE]\n\n"
+            finally:
+                gen.close()        # client gone before the last chunk: the router cancels the request and frees its decode row
 
         return StreamingResponse(events(), media_type="text/event-stream")
 
