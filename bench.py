@@ -10,18 +10,28 @@ K1 admission (rpm/tpm debit + least-busy pick) -> per-GPU engine: chunked prefil
 
   value      completions/s from device time only: CUDA events on each engine's stream around every
              prefill chunk and every decode step of the timed steps (inputs resident), max over ranks.
-  e2e        the same metric by host wall clock through the public API (Router.completion_batch /
-             rr_router_process + rr_engine_submit/wait): prompts start in pinned HOST memory, admission
-             events H2D, decisions D2H, prompt ids H2D, generated tokens D2H all inside the timed region.
-  roofline   decode step (one CUDA-graph launch = the dominant unit, ~78 % of step time): algorithmic bytes
-             (weights streamed once + KV read) / mean CUDA-event step time, against MEASURED_PEAKS.json.
+  e2e        the same metric by host wall clock through the public API: prompts start in pinned HOST memory,
+             admission events H2D, decisions D2H, prompt ids H2D, generated tokens D2H all inside the timed region.
+             N = 1: Router.completion_batch (native gateway: rr_gateway_submit_batch / rr_gateway_wait);
+             N > 1: rank 0 admits with rr_router_process, assignments travel by NCCL, every rank serves its share
+             with rr_engine_run_batch.
+  roofline   decode step (one CUDA-graph launch = the dominant unit): algorithmic bytes
+             (weights streamed once + KV read) / mean CUDA-event step time, against MEASURED_PEAKS.json;
+             `kernels` = per-kernel table (algorithmic bytes, in-graph critical-path us, fraction of peak) from the
+             library's in-kernel timeline, taken AFTER the timed region.
+  per_request / http (N = 1, after the timed region): the same burst issued by 64 concurrent Router.completion()
+             callers, and by 64 OpenAI-SDK clients over HTTP against the in-process gateway (server.py).
   cpu_baseline / --impl reference: the CPU restatement (oracle/) of the same path timed on the box's host
              cores on a bounded sample (the reference's own router, litellm, cannot be installed:
              BASELINE.md §2; there is no baseline/_ref).
+
+Other BASELINE.json configs (single process driving --gpus N devices through the native gateway, the layout of the
+reference's one-process gateway):  --config quota | fallback | fleet   (see run_fleet).
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -36,9 +46,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "completions/sec (512-in/128-out, Llama-3-8B, 64 concurrent per GPU)"
-# DRAM traffic of one decode step (64 rows, ctx 577) from the committed ncu --set full captures: per layer
-# qkv 50.9 + o 34.1 + gate/up 238.6 + down 122.9 + attention 159.1 MB, x32, + lm_head 1.08 GB (algorithmic: 19.84 GB)
-DECODE_STEP_DRAM_BYTES_NCU = int(32 * (50.91 + 34.12 + 238.55 + 122.92 + 159.14) * 1e6 + 1.083e9)
+CONFIGS = {"1": "headline", "headline": "headline", "2": "quota", "quota": "quota", "3": "fallback", "fallback": "fallback",
+           "4": "fleet", "fleet": "fleet"}
 
 
 def parse_args():
@@ -52,6 +61,10 @@ def parse_args():
     ap.add_argument("--prompt-len", type=int, default=512)
     ap.add_argument("--max-new", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-request / HTTP / per-kernel legs after the timed region")
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: headline (#1, default), quota (#2), fallback (#3), fleet (#4)")
+    ap.add_argument("--trace-out", default=None, help="fleet configs: write the recorded admission trace here (JSON)")
     return ap.parse_args()
 
 
@@ -62,6 +75,17 @@ def load_peaks():
             d = json.load(f)
         return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def load_models_module():
+    """models.py (specs only) WITHOUT importing the package: the package __init__ dlopens librr_b200.so, and the
+    reference arm must not touch this repo's native code."""
+    spec = importlib.util.spec_from_file_location(
+        "_rr_models_only", os.path.join(ROOT, "sample-resilient-llm-inference_b200", "models.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_rr_models_only"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,6 +147,17 @@ def make_prompts(n_req: int, prompt_len: int, vocab: int, pinned: bool):
         g = torch.Generator().manual_seed(1234 + r)
         buf[r] = torch.randint(0, vocab, (prompt_len,), generator=g, dtype=torch.int32)
     return buf
+
+
+def executed_prefill_flops(spec, n_prompts: int, prompt_len: int) -> int:
+    """FLOPs the prefill of one burst EXECUTES (linear layers only): every layer's QKV on all tokens; O / gate-up / down
+    on all tokens for layers 0..L-2; the last layer's O / MLP and the lm_head only on the last token of each prompt
+    (csrc/rr_engine.cu: trimmed tail).  SURVEY 8(d)'s 15.01 GFLOP/token counts lm_head and a full last layer per token."""
+    H, KV, D, hid, inter, L = spec.n_heads, spec.n_kv_heads, spec.head_dim, spec.hidden, spec.inter, spec.n_layers
+    qkv = hid * (H + 2 * KV) * D
+    rest = H * D * hid + 3 * hid * inter
+    T = n_prompts * prompt_len
+    return 2 * (T * (L * qkv + (L - 1) * rest) + n_prompts * (rest + spec.vocab * hid))
 
 
 def cpu_port_sample(spec, prompt_len, max_new, concurrency, n_gpus, layers_timed=4, decode_steps_timed=2, threads=None):
@@ -197,12 +232,12 @@ def cpu_port_sample(spec, prompt_len, max_new, concurrency, n_gpus, layers_timed
 
 # ------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
-    """CPU restatement of the path (the reference's litellm.Router cannot be installed: BASELINE.md §2)."""
+    """CPU restatement of the path (the reference's litellm.Router cannot be installed: BASELINE.md §2).  Pure torch-CPU +
+    oracle/: nothing of this repo's package (and therefore none of its native code) is imported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from rr_b200.models import resolve_spec
-    spec = resolve_spec(args.model)
+    spec = load_models_module().resolve_spec(args.model)
     vals = []
     sample, cores = "", 0
     t_all = time.perf_counter()
@@ -225,16 +260,187 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak):
+    """Per-kernel share of one decode step from the library's in-kernel timeline (CTA 0 of every kernel stamps
+    %globaltimer at start / when griddepcontrol.wait returns / at exit; rr_debug_trace_*).  The critical-path time of
+    kernel k inside the replayed graph = (dependency of kernel k+1 resolved) - (dependency of kernel k resolved).
+    Runs one short extra burst AFTER the timed region."""
+    import ctypes as Ct
+    from rr_b200 import _lib
+    NAMES = {1: "gemm/layer (tcgen05)", 3: "decode_attn", 5: "add_rmsnorm", 8: "embed", 9: "argmax", 10: "attn_combine"}
+    ids = np.ascontiguousarray(prompts_np[:C]).reshape(-1)
+    start = np.arange(0, (C + 1) * P, P, dtype=np.int32)
+    N = 20000
+    _lib.check(_lib.lib.rr_debug_trace_start(N), "trace_start")
+    eng.run_batch(ids, start, 6)
+    buf = (Ct.c_uint64 * (4 * N))(); n = Ct.c_int32()
+    _lib.check(_lib.lib.rr_debug_trace_stop(buf, N, Ct.byref(n)), "trace_stop")
+    a = np.frombuffer(buf, dtype=np.uint64)[: 4 * n.value].reshape(-1, 4).astype(np.int64)
+    a = a[a[:, 0] < 12]                                        # kernel records only
+    a = a[np.argsort(a[:, 1], kind="stable")]
+    emb = np.nonzero(a[:, 0] == 8)[0]
+    if len(emb) < 2:
+        return None
+    step = a[emb[-2]: emb[-1] + 1]                             # one whole decode step + the next step's first kernel
+    L = spec.n_layers
+    H, KV, D, hid, inter = spec.n_heads, spec.n_kv_heads, spec.head_dim, spec.hidden, spec.inter
+    w_qkv, w_o, w_mlp, w_head = 2 * hid * (H + 2 * KV) * D, 2 * H * D * hid, 2 * 3 * hid * inter, 2 * spec.vocab * hid
+    ctx = P + 3                                                # context of the traced steps (3rd..5th generated token)
+    kv_layer = C * ctx * spec.kv_bytes_per_token // L
+    rows = {}
+    n_gemm = 0
+    gemm_total = int((step[:-1, 0] == 1).sum())
+    for i in range(len(step) - 1):
+        kid = int(step[i, 0])
+        seg_us = (step[i + 1, 2] - step[i, 2]) / 1e3
+        name, nbytes = NAMES.get(kid, f"kernel {kid}"), 0
+        if kid == 3:
+            nbytes = kv_layer
+        elif kid == 1:
+            if gemm_total == L + 1:                            # persistent layer kernels: QKV_0 | layer l (+ QKV_{l+1}) | last (+ lm_head)
+                if n_gemm == 0:
+                    name, nbytes = "decode_layer_tcgen05 [QKV of layer 0]", w_qkv
+                elif n_gemm < L:
+                    name, nbytes = "decode_layer_tcgen05 [O + gate/up + down + next QKV]", w_o + w_mlp + w_qkv
+                else:
+                    name, nbytes = "decode_layer_tcgen05 [last layer + lm_head]", w_o + w_mlp + w_head
+            else:
+                name = "gemm_bf16_tcgen05 / gemm_mlp_tcgen05 (unfused path)"
+            n_gemm += 1
+        r = rows.setdefault(name, {"kernel": name, "launches": 0, "us": 0.0, "bytes": 0})
+        r["launches"] += 1; r["us"] += seg_us; r["bytes"] += nbytes
+    out = []
+    for r in rows.values():
+        gbs = r["bytes"] / (r["us"] * 1e-6) / 1e9 if r["bytes"] and r["us"] > 0 else None
+        out.append({"kernel": r["kernel"], "launches": r["launches"], "us_per_launch": r["us"] / r["launches"],
+                    "us_per_step": r["us"], "algorithmic_bytes_per_launch": r["bytes"] // r["launches"],
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": (gbs / hbm_peak) if gbs else None})
+    out.sort(key=lambda x: -x["us_per_step"])
+    return {"step_us": float((step[-1, 2] - step[0, 2]) / 1e3), "ctx": ctx, "rows": out,
+            "method": "in-kernel %globaltimer stamps of CTA 0 (rr_debug_trace_*), critical-path segments inside the replayed CUDA graph"}
+
+
+def per_request_leg(router, model, prompts_np, n_req, M, bursts=2):
+    """The same closed burst issued the way the reference's demos do it: one blocking call per client thread."""
+    lat, ttft, errs = [], [], []
+    st0 = router.gateway_stats()
+    t0 = time.perf_counter()
+    for _ in range(bursts):
+        out = [None] * n_req
+
+        def work(i):
+            try:
+                out[i] = router.completion(model=model, prompt_ids=prompts_np[i], max_tokens=M, timeout=300)
+            except Exception as e:                              # noqa: BLE001 (recorded, re-raised below)
+                out[i] = e
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(n_req)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for o in out:
+            if isinstance(o, Exception):
+                errs.append(repr(o))
+            else:
+                assert len(o._token_ids) == M
+                lat.append(o._latency_s); ttft.append(o._ttft_s)
+    wall = time.perf_counter() - t0
+    router.snapshot()
+    st1 = router.gateway_stats()
+    ev, la = st1["events"] - st0["events"], st1["launches"] - st0["launches"]
+    return {"api": "Router.completion() from %d concurrent threads (rr_gateway_submit / rr_gateway_wait)" % n_req,
+            "value": len(lat) / wall, "unit": "completions/s", "bursts": bursts, "errors": errs[:3],
+            "p50_ttft_ms": float(np.percentile(ttft, 50) * 1e3), "p99_ttft_ms": float(np.percentile(ttft, 99) * 1e3),
+            "p50_latency_ms": float(np.percentile(lat, 50) * 1e3),
+            "k1_launches": int(la), "k1_events": int(ev), "events_per_launch": ev / max(1, la),
+            "admit_wait_us_mean": 1e6 * (st1["admit_wait_s"] - st0["admit_wait_s"]) / max(1, st1["submitted"] - st0["submitted"])}
+
+
+def k1_single_event_latency(router, reps=200):
+    """One ADMIT + one DONE through rr_router_process (H2D + launch + D2H + sync each): the un-coalesced per-event cost."""
+    now = router.now_ms()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        (st, dep, _, _), = router.process([(0, 0, 512, 0, now)])
+        router.process([(1, dep, 128, 0, now)])
+    return (time.perf_counter() - t0) * 1e6 / (2 * reps)
+
+
+def http_leg(router, model, prompts_np, n_req, M):
+    """64 OpenAI-SDK clients (the reference's client boundary: src/demo_load_balancing.py:24,106-110) streaming from the
+    in-process gateway; TTFT = first SSE chunk."""
+    try:
+        import openai
+        import uvicorn
+        from rr_b200.server import create_app
+        from rr_b200.router import detokenize
+    except Exception as e:                                      # noqa: BLE001
+        return {"skipped": repr(e)}
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    server = uvicorn.Server(uvicorn.Config(create_app(router), host="127.0.0.1", port=port, log_level="error"))
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    t_wait = time.time()
+    while not server.started and time.time() - t_wait < 30:
+        time.sleep(0.05)
+    # prompts travel as text over HTTP: byte-level tokenizer -> a 511-character message is 512 tokens ("user: " + text + BOS)
+    text = ["".join(chr(97 + int(t) % 26) for t in prompts_np[i][: P_TEXT]) for i in range(n_req)]
+    out, ttft, lat = [None] * n_req, [], []
+    lock = threading.Lock()
+
+    def work(i):
+        client = openai.OpenAI(api_key="demo-key", base_url=f"http://127.0.0.1:{port}", max_retries=0)
+        t0 = time.perf_counter()
+        first, n_chunks = None, 0
+        try:
+            stream = client.chat.completions.create(model=model, messages=[{"role": "user", "content": text[i]}],
+                                                    max_tokens=M, stream=True, timeout=300)
+            for ch in stream:
+                if first is None:
+                    first = time.perf_counter() - t0
+                n_chunks += 1
+            with lock:
+                ttft.append(first); lat.append(time.perf_counter() - t0)
+            out[i] = n_chunks
+        except Exception as e:                                  # noqa: BLE001
+            out[i] = e
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_req)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    server.should_exit = True
+    th.join(timeout=10)
+    errs = [repr(o) for o in out if isinstance(o, Exception)]
+    if not lat:
+        return {"errors": errs[:3]}
+    return {"api": "openai.OpenAI(base_url=http://127.0.0.1:<port>).chat.completions.create(stream=True) x %d threads" % n_req,
+            "value": len(lat) / wall, "unit": "completions/s", "errors": errs[:3],
+            "p50_ttft_ms": float(np.percentile(ttft, 50) * 1e3), "p99_ttft_ms": float(np.percentile(ttft, 99) * 1e3),
+            "p50_latency_ms": float(np.percentile(lat, 50) * 1e3), "prompt_tokens": P_TEXT + 7}
+
+
+P_TEXT = 505          # "user: " (6) + 505 characters + BOS = 512 tokens of the byte-level tokenizer
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    kind = CONFIGS[args.config]
+    if kind != "headline":
+        run_fleet(args, kind)
+        return
     import torch
     import torch.distributed as dist
     from rr_b200.models import resolve_spec, make_weights, broadcast_weights
     from rr_b200.engine import Engine
-    from rr_b200.router import Router, EngineBackend, RateLimitError
+    from rr_b200.router import Router, EngineBackend
     from rr_b200 import parallel
 
     rank = int(os.environ.get("RANK", "0"))
@@ -278,17 +484,21 @@ def main():
     prompts_np = prompts.numpy()
 
     ttfts, lat = [], []
+    token_sums = []                                                # per step: checksum of every generated token
 
     def one_step(collect: bool):
         """One closed burst through the public path.  Returns nothing; per-request timings collected."""
         if world == 1:
             out = router.completion_batch(args.model, [prompts_np[i] for i in range(n_req)], M)
-            for r in out:
+            chk = 0
+            for i, r in enumerate(out):
                 if isinstance(r, Exception):
                     raise r
-                assert len(r._token_ids) == M
+                assert len(r._token_ids) == M and all(0 <= t < spec.vocab for t in r._token_ids)
+                chk = (chk * 1000003 + hash(tuple(r._token_ids)) + i) & 0xFFFFFFFFFFFF
                 if collect:
                     ttfts.append(r._ttft_s); lat.append(r._latency_s)
+            token_sums.append(chk)
         else:
             dec = None
             if rank == 0:
@@ -300,6 +510,7 @@ def main():
             start = np.arange(0, (len(mine) + 1) * P, P, dtype=np.int32)
             recs, _ = eng.run_batch(ids, start, M) if len(mine) else ([], None)
             assert all(r.status == 0 and len(r.tokens) == M for r in recs)
+            token_sums.append(hash(tuple(tuple(r.tokens) for r in recs)) & 0xFFFFFFFFFFFF)
             if collect:
                 ttfts.extend(r.ttft for r in recs); lat.extend(r.latency for r in recs)
             parallel.gather_done(len(mine), world, rank, device=torch.device("cuda", local))
@@ -329,6 +540,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
     dev_s = (st["prefill_ms_total"] + st["decode_ms_total"]) / 1e3
+    # identical prompts every step and deterministic kernels: every step must have generated exactly the same tokens
+    # (the assignment of requests to ranks is deterministic too)
+    assert len(set(token_sums)) == 1, "generated tokens differ between bursts"
 
     # ---- max over ranks
     vals = torch.tensor([wall, dev_s, st["decode_ms_total"], float(st["decode_steps"]), st["prefill_ms_total"],
@@ -357,8 +571,19 @@ def main():
         bytes_step = spec.weight_bytes_per_decode_step + C * mean_ctx * spec.kv_bytes_per_token
         dec_ms = mx[2].item() / max(1.0, mx[3].item())
         achieved = bytes_step / (dec_ms * 1e-3) / 1e9
-        pf_tokens = C * P * K
-        pf_tflops = spec.prefill_flops_per_token * pf_tokens / (mx[4].item() * 1e-3) / 1e12 if mx[4].item() > 0 else None
+        pf_ms = mx[4].item()
+        flops_exec = executed_prefill_flops(spec, C, P) * K
+        flops_survey = spec.prefill_flops_per_token * C * P * K
+        pf_tflops = flops_exec / (pf_ms * 1e-3) / 1e12 if pf_ms > 0 else None
+        launches_per_step = int(st["kernel_launches"] / max(1, st["decode_steps"] + st["prefill_chunks"]))
+        # DRAM traffic of one decode step: from the committed ncu --set full capture of THIS code, if one exists
+        traffic, traffic_src = None, "no ncu capture of the current decode step committed (profiles/r02_decode_step_traffic.json)"
+        tp = os.path.join(ROOT, "profiles", "r02_decode_step_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("model") == args.model and tj.get("rows") == C and tj.get("prompt_len") == P:
+                traffic, traffic_src = tj.get("dram_bytes_per_step"), tj.get("source")
         line = {
             "metric": METRIC, "value": total_completions / dev_max, "unit": "completions/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * dev_max / K, "higher_is_better": True,
@@ -372,23 +597,40 @@ def main():
             "tokens_per_s": total_completions * M / dev_max,
             "e2e": {"value": total_completions / wall_max, "unit": "completions/s", "ms_per_step": 1e3 * wall_max / K,
                     "h2d_bytes_per_step": int(sm[6].item() / K + 24 * n_req), "d2h_bytes_per_step": int(sm[7].item() / K + 16 * n_req),
-                    "api": "Router.completion_batch -> rr_router_process + rr_engine_submit/rr_engine_wait (host buffers)"},
+                    "api": ("Router.completion_batch -> rr_gateway_submit_batch / rr_gateway_wait (host buffers; K1 + engine hand-off "
+                            "inside the library)") if world == 1 else
+                           ("rank 0: Router.process (rr_router_process, host buffers) -> NCCL broadcast of the assignment vector -> "
+                            "every rank: Engine.run_batch (rr_engine_run_batch, host buffers) -> NCCL all-reduce -> DONE trace")},
             "gpu_launches": int(sm[5].item() + 2 * K),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": DECODE_STEP_DRAM_BYTES_NCU if (args.model == "llama-3-8b" and C == 64 and P == 512 and M == 128) else None,
-                         "traffic_source": "sum over the step's kernels of dram__bytes_read+write from ncu --set full (profiles/r01_ncu_full_summary.txt)",
-                         "kernel": "decode step = 1 CUDA-graph launch (196 kernels with PDL edges; dominant: gemm_mlp_tcgen05<64> / gemm_bf16_tcgen05<64,*> weight streams)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "decode step = 1 CUDA-graph launch; dominant kernels: decode_layer_tcgen05<64> (weight stream of one "
+                                   "layer + next QKV, 32 launches) and decode_attn_mma_kernel<4> (KV stream, 32 launches)",
                          "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms, "peak_source": peak_src},
             "prefill": {"tflops": pf_tflops, "peak_tflops_sustained": tf_peak, "frac": (pf_tflops / tf_peak) if pf_tflops else None,
-                        "ms_per_burst": mx[4].item() / K},
+                        "ms_per_burst": pf_ms / K, "flops_counted": "executed (last layer's O / MLP and lm_head only on each prompt's last token)",
+                        "gflop_per_token_executed": flops_exec / (C * P * K) / 1e9,
+                        "gflop_per_token_survey_8d": spec.prefill_flops_per_token / 1e9,
+                        "frac_with_survey_8d_flops": (flops_survey / (pf_ms * 1e-3) / 1e12 / tf_peak) if pf_ms > 0 else None},
+            "launches_per_decode_step_or_chunk_mean": launches_per_step,
             "clocks": clocks, "init_s": init_s, "weight_broadcast_s": bcast_s,
         }
         # K1 (router kernel) is latency-bound, not roofline-bound: report time per event of a full trace
         try:
             line["router"] = router_kernel_timing(router)
+            line["router"]["us_per_event_single_launch"] = k1_single_event_latency(router)
         except Exception as ex:                                   # never lose the headline line over the side measurement
             line["router"] = {"error": repr(ex)}
+        if world == 1 and not args.no_extras:
+            for key, fn in (("per_request", lambda: per_request_leg(router, args.model, prompts_np, n_req, M)),
+                            ("http", lambda: http_leg(router, args.model, prompts_np, n_req, M)),
+                            ("kernels", lambda: kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak))):
+                try:
+                    line[key] = fn()
+                except Exception as ex:                           # noqa: BLE001
+                    line[key] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
+            router.close()
             eng.close()
             v, sample, cores = cpu_port_sample(spec, P, M, C, world)
             line["cpu_baseline"] = {"value": v, "unit": "completions/s", "cores": cores, "kind": "port", "sample": sample}
@@ -434,6 +676,244 @@ def router_kernel_timing(router, n_events: int = 2048, reps: int = 5):
     host_ns = (time.perf_counter() - t0) * 1e9 / (reps * n_events)
     return {"events_per_launch": n_events, "ns_per_event_device": dev_ns, "events_per_s_device": 1e9 / dev_ns,
             "ns_per_event_host_api": host_ns, "bound": "latency (one warp walks the trace in order; lanes = candidate deployments)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs #2-#4: ONE process drives all --gpus devices through the native gateway (rr_gateway.cu), one
+# engine (worker thread) per GPU -- the reference's deployment shape (one gateway process, bin/start-gateway.sh:54).
+def fleet_plan(kind, n_gpus, C, P, M, steps):
+    """-> (model_list, router settings, engines {gpu: (spec name, fail_prob)}, workload [(group name, n requests)], notes)."""
+    if kind == "quota":
+        # config #2: N replicas, 64 N concurrent requests, rpm/tpm buckets + three teams with separate groups
+        # (reference config/config.yaml:74-94: one model group = one rpm bucket per consumer).  Team A asks for 25 % more than
+        # its rpm admits.
+        share = {"a": 3, "b": 3, "c": 2}                               # of every 8 GPUs / of every 512 requests
+        total = C * n_gpus
+        gpus = list(range(n_gpus))
+        owned = {"a": [], "b": [], "c": []}
+        for i, g in enumerate(gpus):
+            owned["a" if i % 8 < 3 else ("b" if i % 8 < 6 else "c")].append(g)
+        for t in owned:                                                 # fewer than 8 GPUs: teams share replicas
+            if not owned[t]:
+                owned[t] = [gpus[hash(t) % n_gpus]] if n_gpus > 1 else [0]
+        n_team = {t: total * share[t] // 8 for t in share}
+        ml = []
+        for t in "abc":
+            # rpm window must admit `steps + warmup` bursts: the bench gives each burst its own minute (manual clock)
+            per_dep = -(-n_team[t] // len(owned[t]))
+            rpm = per_dep if t != "a" else int(per_dep * 0.75)
+            for g in owned[t]:
+                ml.append({"model_name": f"team-{t}", "litellm_params": {"model": f"b200/llama-3-8b@team-{t}", "gpu": g},
+                           "rpm": rpm, "tpm": rpm * (P + M) * 2})
+        eng = {g: ("llama-3-8b", 0.0) for g in gpus}
+        rs = {"routing_strategy": "simple-shuffle", "enable_pre_call_checks": True, "allowed_fails": 2, "cooldown_time": 15}
+        work = [(f"team-{t}", n_team[t]) for t in "abc"]
+        return ml, rs, eng, work, {"expect": "about 25 % of team-a's requests answer 429; teams b and c are untouched"}
+    if kind == "fallback":
+        # config #3: Llama-3-8B primary with a seeded 50 % failure mask, Phi-3-mini fallback (reference config.yaml:103-108)
+        g1 = 1 if n_gpus > 1 else 0
+        ml = [{"model_name": "primary", "litellm_params": {"model": "b200/llama-3-8b", "gpu": 0}},
+              {"model_name": "fallback", "litellm_params": {"model": "b200/phi-3-mini", "gpu": g1 if n_gpus > 1 else 1}}]
+        eng = {0: ("llama-3-8b", 0.5), (g1 if n_gpus > 1 else 1): ("phi-3-mini", 0.0)}
+        rs = {"routing_strategy": "simple-shuffle", "enable_pre_call_checks": True, "allowed_fails": 1_000_000,
+              "cooldown_time": 15, "fallbacks": [{"primary": ["fallback"]}]}
+        return ml, rs, eng, [("primary", C * max(1, n_gpus // 2))], {"fail_prob": 0.5, "fail_seed": 42}
+    # config #4: mixed fleet, Llama-3-8B on 3/4 of the GPUs, Mistral-7B on the rest; weighted simple-shuffle, every
+    # deployment weight 1 => 3 : 1 between the fleets; 1 000-request soak, Poisson arrivals
+    n_l = max(1, (3 * n_gpus) // 4) if n_gpus > 1 else 1
+    ml, eng = [], {}
+    for g in range(max(2, n_gpus)):
+        is_l = g < n_l
+        gpu = g if n_gpus > 1 else g                                  # n_gpus == 1: two engines on device 0 (see run_fleet)
+        ml.append({"model_name": "chat", "litellm_params": {"model": "b200/" + ("llama-3-8b" if is_l else "mistral-7b"),
+                                                             "gpu": gpu, "weight": 1}})
+        eng[gpu] = ("llama-3-8b" if is_l else "mistral-7b", 0.0)
+    rs = {"routing_strategy": "simple-shuffle", "enable_pre_call_checks": False, "allowed_fails": 2, "cooldown_time": 15}
+    return ml, rs, eng, [("chat", 1000)], {"arrivals": "poisson"}
+
+
+def run_fleet(args, kind):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                                          # one process drives every GPU
+    import torch
+    from rr_b200.models import resolve_spec, make_weights, Weights
+    from rr_b200.engine import Engine
+    from rr_b200.router import Router, EngineBackend, RateLimitError, APIError
+
+    n_gpus = min(args.gpus, torch.cuda.device_count())
+    C, P, M, K, W = args.concurrency, args.prompt_len, args.max_new, args.steps, args.warmup
+    ml, rs, eng_plan, work, notes = fleet_plan(kind, n_gpus, C, P, M, K)
+    ctx_max = ((P + M + 63) // 64) * 64
+    t0 = time.perf_counter()
+    base = {}                                                           # spec name -> weights on their first device
+    engines, backends = {}, {}
+    for replica, (name, fail_prob) in sorted(eng_plan.items()):
+        dev = replica if replica < n_gpus else 0
+        if name not in base:
+            base[name] = make_weights(resolve_spec(name), seed=0, sigma=0.02, device=f"cuda:{dev}")
+            w = base[name]
+        else:
+            w = base[name].to(f"cuda:{dev}") if str(base[name].embed.device) != f"cuda:{dev}" else base[name]
+        engines[replica] = Engine(w, device=dev, max_batch=C, ctx_max=ctx_max, max_prefill_tokens=8192, use_cuda_graph=True,
+                                  fail_prob=fail_prob, fail_seed=42)
+        backends[replica] = EngineBackend(engines[replica])
+    init_s = time.perf_counter() - t0
+    now = [1_000_000.0]
+    router = Router(model_list=ml, routing_strategy=rs["routing_strategy"], enable_pre_call_checks=rs["enable_pre_call_checks"],
+                    allowed_fails=rs["allowed_fails"], cooldown_time=rs["cooldown_time"], fallbacks=rs.get("fallbacks"),
+                    backends=backends, seed=0, clock=lambda: now[0])
+    router.record_trace = 1 << 16
+    vocab = router._vocab()
+    n_max = max(n for _, n in work)
+    prompts = make_prompts(n_max, P, vocab, pinned=True).numpy()
+    for e in engines.values():
+        e.reset_stats()
+
+    def burst(collect, res):
+        """All groups' requests issued together by one thread per group (completion_batch = one contiguous trace block)."""
+        outs = {}
+
+        def go(gname, n):
+            outs[gname] = router.completion_batch(gname, [prompts[i] for i in range(n)], M, timeout=600)
+        ths = [threading.Thread(target=go, args=w_) for w_ in work]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if collect:
+            for gname, out in outs.items():
+                r = res.setdefault(gname, {"ok": 0, "rate_limited": 0, "failed": 0, "fell_back": 0, "ttft": [], "lat": [], "by_model": {}})
+                for o in out:
+                    if isinstance(o, RateLimitError):
+                        r["rate_limited"] += 1
+                    elif isinstance(o, Exception):
+                        r["failed"] += 1
+                    else:
+                        assert len(o._token_ids) == M
+                        r["ok"] += 1; r["fell_back"] += int(o._fell_back)
+                        r["ttft"].append(o._ttft_s); r["lat"].append(o._latency_s)
+                        r["by_model"][o.model] = r["by_model"].get(o.model, 0) + 1
+
+    def soak(collect, res, n, rate):
+        """Open loop: n requests with exponential inter-arrival times at `rate` req/s, one caller thread each."""
+        rng = np.random.RandomState(7)
+        gaps = rng.exponential(1.0 / rate, size=n)
+        out = [None] * n
+
+        def one(i):
+            try:
+                out[i] = router.completion(model="chat", prompt_ids=prompts[i], max_tokens=M, timeout=600)
+            except Exception as e:                                      # noqa: BLE001
+                out[i] = e
+        ths = []
+        t_next = time.perf_counter()
+        for i in range(n):
+            t_next += gaps[i]
+            d = t_next - time.perf_counter()
+            if d > 0:
+                time.sleep(d)
+            th = threading.Thread(target=one, args=(i,))
+            th.start(); ths.append(th)
+        for th in ths:
+            th.join()
+        if collect:
+            r = res.setdefault("chat", {"ok": 0, "rate_limited": 0, "failed": 0, "fell_back": 0, "ttft": [], "lat": [], "by_model": {}})
+            for o in out:
+                if isinstance(o, Exception):
+                    r["failed"] += 1
+                else:
+                    r["ok"] += 1; r["ttft"].append(o._ttft_s); r["lat"].append(o._latency_s)
+                    r["by_model"][o.model] = r["by_model"].get(o.model, 0) + 1
+
+    res = {}
+    n_rep = len(engines)
+    if kind == "fleet":
+        cap = 70.0 * n_rep * (64.0 / C if C else 1.0)                   # completions/s the fleet sustains (closed-burst figure)
+        rate = 0.8 * cap
+        soak(False, res, min(200, 64 * n_rep), rate)                    # warm-up (graph capture, first prefill plans)
+        for e in engines.values():
+            e.reset_stats()
+        router.snapshot()
+        sampler = ClockSampler(0); sampler.start()
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        soak(True, res, work[0][1], rate)
+        wall = time.perf_counter() - t_start
+        steps_done = 1
+    else:
+        for _ in range(W):
+            now[0] += 60.0                                              # every burst gets a fresh rpm / tpm minute
+            burst(False, res)
+        for e in engines.values():
+            e.reset_stats()
+        router.snapshot()
+        sampler = ClockSampler(0); sampler.start()
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        for _ in range(K):
+            now[0] += 60.0
+            burst(True, res)
+        wall = time.perf_counter() - t_start
+        steps_done = K
+    clocks = sampler.stop()
+    snap = router.snapshot()
+    gstats = router.gateway_stats()
+    trace = router.gateway_trace()
+    dev_ms = max((e.stats()["prefill_ms_total"] + e.stats()["decode_ms_total"]) for e in engines.values())
+    launches = sum(e.stats()["kernel_launches"] for e in engines.values()) + gstats["launches"]
+    total_ok = sum(r["ok"] for r in res.values())
+    all_ttft = np.asarray([t for r in res.values() for t in r["ttft"]])
+    line = {"metric": f"completions/sec & TTFT, BASELINE config '{kind}' ({P}-in/{M}-out)", "value": total_ok / (dev_ms / 1e3) if dev_ms else None,
+            "unit": "completions/s", "n_gpus": n_gpus, "steps": steps_done, "warmup": W, "ms_per_step": dev_ms / max(1, steps_done),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": kind, "model_list": [(d["model_name"], d["litellm_params"]["model"], d["litellm_params"]["gpu"],
+                                                          d.get("rpm"), d.get("tpm")) for d in ml],
+                       "router_settings": rs, "requests_per_step": {g: n for g, n in work}, "notes": notes,
+                       "process_layout": f"one process, {n_rep} engines on {n_gpus} GPU(s), native gateway"},
+            "e2e": {"value": total_ok / wall, "unit": "completions/s", "wall_s": wall,
+                    "api": "Router.completion_batch / Router.completion -> rr_gateway_* (host buffers)",
+                    "h2d_bytes_per_step": int(sum(e.stats()["h2d_bytes"] for e in engines.values()) / max(1, steps_done)),
+                    "d2h_bytes_per_step": int(sum(e.stats()["d2h_bytes"] for e in engines.values()) / max(1, steps_done))},
+            "p50_ttft_ms": float(np.percentile(all_ttft, 50) * 1e3) if len(all_ttft) else None,
+            "p99_ttft_ms": float(np.percentile(all_ttft, 99) * 1e3) if len(all_ttft) else None,
+            "groups": {g: {"ok": r["ok"], "rate_limited": r["rate_limited"], "failed": r["failed"], "fell_back": r["fell_back"],
+                           "by_model": r["by_model"],
+                           "p50_ttft_ms": float(np.percentile(r["ttft"], 50) * 1e3) if r["ttft"] else None,
+                           "p99_ttft_ms": float(np.percentile(r["ttft"], 99) * 1e3) if r["ttft"] else None} for g, r in res.items()},
+            "gateway": gstats, "gpu_launches": int(launches),
+            "deployments": [{"model": d.response_model, "gpu": d.gpu, "total_admitted": s["total_admitted"], "fail_count": s["fail_count"],
+                             "inflight": s["inflight"]} for d, s in zip(router.cfg.deployments, snap)],
+            "decode_ms_per_step": {str(g): (e.stats()["decode_ms_total"] / max(1, e.stats()["decode_steps"])) for g, e in engines.items()},
+            "clocks": clocks, "init_s": init_s}
+    if args.trace_out:
+        with open(args.trace_out, "w") as f:
+            json.dump({"kind": kind, "seed": 0, "model_list": ml, "router_settings": rs,
+                       "trace": [[list(e), list(d)] for e, d in trace]}, f)
+        line["trace_file"] = args.trace_out
+    router.close()
+    for e in engines.values():
+        e.close()
+    if not args.no_cpu_baseline:
+        # checker + CPU baseline of the ROUTER path on the recorded trace: the oracle replays every event; decisions must be
+        # bit-exact with what K1 decided on the device
+        from oracle import router as O
+        from rr_b200.config import build_config
+        cfg = build_config(ml, rs)
+        deps = [O.Deployment(d.group, rpm=d.rpm, tpm=d.tpm, weight=d.weight) for d in cfg.deployments]
+        orc = O.OracleRouter(deps, len(cfg.groups), dict(cfg.fallbacks),
+                             O.Settings(strategy=cfg.strategy_id, enable_pre_call_checks=cfg.enable_pre_call_checks,
+                                        allowed_fails=cfg.allowed_fails, cooldown_ms=int(round(cfg.cooldown_time * 1000))), seed=0)
+        t0 = time.perf_counter()
+        want = orc.process([O.Event(*e) for e, _ in trace])
+        dt = time.perf_counter() - t0
+        n_adm = sum(1 for e, _ in trace if e[0] == 0)
+        exact = all(w_.as_tuple() == tuple(d) for w_, (e, d) in zip(want, trace) if e[0] == 0)
+        line["cpu_baseline"] = {"value": n_adm / dt if dt > 0 else None, "unit": "admissions/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle/router.py replay of the {len(trace)} recorded events ({n_adm} admissions) of this run",
+                                "decisions_bit_exact": bool(exact), "trace_complete": len(trace) == gstats["events"]}
+        assert exact, "K1 decisions differ from the oracle on the recorded trace"
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

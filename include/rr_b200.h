@@ -51,6 +51,8 @@ int rr_set_pdl(int enabled);
  * (4 x uint64 each) to `out`. */
 int rr_debug_trace_start(int max_entries);
 int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n);
+/* on != 0: sample CTAs of the persistent decode layer kernel also record one mark per finished work item (kernel id 12 + phase). */
+int rr_debug_trace_detail(int on);
 /* Host-side work schedule of the fused decode MLP kernel (gate/up + down GEMMs in one launch), for
  * inspection and tests; no device is touched.  items_out receives grid * (*max_items) entries of 4 x int32
  * {tile | phase << 16 (phase 0 gate/up, 1 down; -1 = end of the CTA's list), kb0, kb1, slice}, CTA-major;
@@ -239,7 +241,7 @@ typedef struct rr_engine_opts {
     int32_t use_cuda_graph;       /* capture the decode step */
     int32_t fail_seed;            /* fault injection: seed of the Bernoulli failure mask */
     float fail_prob;              /* fault injection: P(request fails) (BASELINE config #4) */
-    int32_t reserved[4];          /* A/B switches: [0] = 1 no persistent decode layer kernel (rr_layer.cu); [1] = 1 no RoPE fusion in the prefill
+    int32_t reserved[4];          /* A/B switches: [0] = 2 persistent decode layer kernel (rr_layer.cu; off by default, measured slower); [1] = 1 no RoPE fusion in the prefill
                                      QKV epilogue; [2] = 1 no fused decode MLP kernel; [3] = 1 prefill RMSNorm as separate kernels instead of deferred into the GEMM epilogues */
 } rr_engine_opts;
 

@@ -120,6 +120,7 @@ PROTOTYPES = {
     "rr_last_cuda_error": (C.c_char_p, []),
     "rr_set_pdl": (C.c_int, [C.c_int]),
     "rr_debug_trace_start": (C.c_int, [C.c_int]),
+    "rr_debug_trace_detail": (C.c_int, [C.c_int]),
     "rr_debug_trace_stop": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, c_i32p]),
     "rr_debug_mlp_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p]),
     "rr_debug_layer_schedule": (C.c_int, [C.c_int] * 9 + [c_i32p, C.c_int, c_i32p]),

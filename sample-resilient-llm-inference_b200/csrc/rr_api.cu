@@ -52,6 +52,7 @@ void rr_trace_set_attn(unsigned long long*);
 void rr_trace_set_attn_tc(unsigned long long*);
 void rr_trace_set_elementwise(unsigned long long*);
 void rr_trace_set_layer(unsigned long long*);
+void rr_trace_set_layer_detail(int);
 }
 static unsigned long long* g_trace_dev = nullptr;
 static int g_trace_cap = 0;
@@ -86,6 +87,12 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
     *n = m;
     cudaFree(g_trace_dev);
     g_trace_dev = nullptr;
+    return check_last();
+}
+
+// Per-item marks of sample CTAs inside the persistent layer kernel (tools/trace_layer.py); off by default.
+RR_API int rr_debug_trace_detail(int on) {
+    rr_trace_set_layer_detail(on ? 1 : 0);
     return check_last();
 }
 

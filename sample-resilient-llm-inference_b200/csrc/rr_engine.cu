@@ -756,8 +756,12 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     // with the earlier row-per-thread epilogue the same fusion LOST 1.4 % (o-proj +35 %).
     e->defer_norm_pf = opts->reserved[3] == 0 && !getenv("RR_NO_DEFER_NORM") && d.hidden % 8 == 0 && e->pf_parts <= 64;
     if (e->defer_norm_pf) TRY(dalloc(e, &e->p_rowss, (size_t)e->Tmax * e->pf_parts));
-    // ---- persistent layer kernel (default when the fused MLP is possible; reserved[0] = 1 / RR_NO_LAYER_FUSE=1: off)
-    e->use_layer = e->fuse_mlp && opts->reserved[0] == 0 && !getenv("RR_NO_LAYER_FUSE");
+    // ---- persistent layer kernel (rr_layer.cu): OFF by default -- reserved[0] = 2 or RR_LAYER_FUSE=1 turns it on.
+    // Measured on B200 (tools/decode_ab.py, same process, alternating): 4.67 ms per decode step against 4.34 ms for the
+    // per-kernel path below.  Under a saturated weight stream every dependent memory round trip costs 2.5 - 4 us (the ring
+    // depth sweep in profiles/r02_layer_kernel_experiment.md), and a dependency counter is 3 - 4 of them (store drain,
+    // release, poll, operand load), while a kernel boundary happens when the memory system has drained.
+    e->use_layer = e->fuse_mlp && (opts->reserved[0] == 2 || getenv("RR_LAYER_FUSE")) && !getenv("RR_NO_LAYER_FUSE");
     if (e->use_layer) {
         const int grid = num_sms();
         const int tiles_h = (d.hidden + 127) / 128, kb_o = (e->nq + 63) / 64;
@@ -802,6 +806,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                     bf.x = e->x; bf.xhat = e->xn; bf.rowss_a = e->rowss_a; bf.rowss_b = e->rowss_b; bf.rows = B; bf.ld_rows = B;
                     bf.eps = d.rms_eps;
                     bf.l2_ahead = getenv("RR_LAYER_L2_AHEAD") ? atoi(getenv("RR_LAYER_L2_AHEAD")) : 0;
+                    bf.ring_depth = getenv("RR_LAYER_RING_DEPTH") ? atoi(getenv("RR_LAYER_RING_DEPTH")) : 0;
                     if (l >= 0) {
                         bf.wo = e->wo[l]; bf.wgu = e->wgu[l]; bf.wdown = e->wdown[l]; bf.attn_out = e->attn_out; bf.act = e->act;
                         bf.part_o = e->part_o; bf.part_d = e->part_down; bf.gamma_a = (const __nv_bfloat16*)e->norm_mlp[l];

@@ -135,6 +135,7 @@ struct LayerBuffers {
     int rows, ld_rows, ldo3;
     float eps;
     int l2_ahead;                               // weight k-blocks prefetched into L2 behind the smem ring while a dependency is awaited
+    int ring_depth;                             // smem ring slots in use (0 = all)
 };
 struct LayerArgs {
     CUtensorMap tmA[4], tmB[4];
@@ -146,7 +147,7 @@ struct LayerArgs {
     float* out3;
     const __nv_bfloat16 *gamma_a, *gamma_b;
     float *rowss_a, *rowss_b;
-    int hidden, inter, rows, ld_rows, rowsA3, ldo3, n_part, tiles_h, s_o, n_slices, slice_kb, rows_red_d, l2_ahead;
+    int hidden, inter, rows, ld_rows, rowsA3, ldo3, n_part, tiles_h, s_o, n_slices, slice_kb, rows_red_d, l2_ahead, ring_depth;
     float inv_hidden, eps;
     const MlpItem* items;     // [grid][max_items]; tile_phase = tile | phase << 16
     int max_items;

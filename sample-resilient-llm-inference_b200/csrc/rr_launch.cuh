@@ -19,7 +19,9 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 // (kernel id, globaltimer at start, after griddepcontrol.wait, at end) into a device buffer; rr_debug_trace_*.
 // Each translation unit owns its copy of the pointer (no -rdc); rr_api.cu sets them all.
 static __device__ unsigned long long* rr_trace_ptr = nullptr;
+static __device__ int rr_trace_detail = 0;      // 1: also per-item marks of sample CTAs (trace_mark_cta), a few % slower
 static inline void rr_trace_set_local(unsigned long long* p) { cudaMemcpyToSymbol(rr_trace_ptr, &p, sizeof(p)); }
+static inline void rr_trace_set_detail_local(int on) { cudaMemcpyToSymbol(rr_trace_detail, &on, sizeof(on)); }
 enum TraceId { TR_GEMM_DEC = 1, TR_GEMM_PF = 2, TR_ATTN_DEC = 3, TR_ATTN_PF = 4, TR_NORM = 5, TR_ROPE = 6,
                TR_SILU = 7, TR_EMBED = 8, TR_ARGMAX = 9, TR_COMBINE = 10, TR_MISC = 11,
                TR_LAYER_PH0 = 12 };  // + k: sample CTAs of the layer kernel finished an item (0 O, 1 gate/up, 2 down, 3 reduce, 4 next)
@@ -54,7 +56,7 @@ __device__ __forceinline__ void trace_mark(int kid) {
 // marker from a few sample CTAs (0, 37, 74, 111, ...): kid in the low byte, CTA index above it
 __device__ __forceinline__ void trace_mark_cta(int kid) {
     unsigned long long* p = rr_trace_ptr;
-    if (p == nullptr || blockIdx.x % 37 != 0) return;
+    if (p == nullptr || rr_trace_detail == 0 || blockIdx.x % 37 != 0) return;
     const int slot = (int)atomicAdd(p, 1ull);
     if (slot >= (int)p[1]) return;
     const unsigned long long t = rr_gtimer();

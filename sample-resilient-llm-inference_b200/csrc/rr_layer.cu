@@ -77,6 +77,9 @@ decode_layer_tcgen05(const __grid_constant__ LayerArgs a) {
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* silu_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+    // Ring slots actually used (<= kStages).  Bytes in flight beyond bandwidth x latency only queue inside the memory system
+    // and delay everything ELSE this SM asks for (dependency counters, reductions, epilogue stores): see DESIGN.md.
+    const int depth = a.ring_depth;
     float* rinv_s = silu_stage + Cfg::kSiluStageBytes / 4;      // [256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,14 +150,14 @@ decode_layer_tcgen05(const __grid_constant__ LayerArgs a) {
                 // Not yet: the WEIGHT tiles of the first stages go out before the wait (and, optionally, an L2 prefetch of
                 // the k-blocks behind them), the activation tiles after it.  Known: plain interleaved A + B issue, so the
                 // ring never drains at an item boundary.
-                const int pre = ok ? 0 : min(kStages, nkb);
+                const int pre = ok ? 0 : min(depth, nkb);
                 const int st0 = stage;
                 for (int j = 0; j < pre; ++j) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, tA, &full_bar[stage], (t.kb0 + j) * BLOCK_K,
                                      t.a_tile * BLOCK_A, polA);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == depth) { stage = 0; phase ^= 1; }
                 }
                 if (!ok) {
                     const int ahead = min(t.kb1, t.kb0 + pre + a.l2_ahead);
@@ -168,14 +171,14 @@ decode_layer_tcgen05(const __grid_constant__ LayerArgs a) {
                 if (ph == 3) d_seen = true;
                 for (int j = 0, s2 = st0; j < pre; ++j) {
                     tma_load_2d_hint(smemB + s2 * Cfg::kStageBytesB, tB, &full_bar[s2], (t.kb0 + j) * BLOCK_K, 0, polB);
-                    if (++s2 == kStages) s2 = 0;
+                    if (++s2 == depth) s2 = 0;
                 }
                 for (int kb = t.kb0 + pre; kb < t.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d_hint(smemA + stage * Cfg::kStageBytesA, tA, &full_bar[stage], kb * BLOCK_K, t.a_tile * BLOCK_A, polA);
                     tma_load_2d_hint(smemB + stage * Cfg::kStageBytesB, tB, &full_bar[stage], kb * BLOCK_K, 0, polB);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == depth) { stage = 0; phase ^= 1; }
                 }
             }
             if (first) { griddep_wait(); trace_dep(tr_slot); }
@@ -201,7 +204,7 @@ decode_layer_tcgen05(const __grid_constant__ LayerArgs a) {
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                         umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == depth) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);
                 ++it;
@@ -549,6 +552,7 @@ int layer_plan_init(LayerPlan* p, const LayerShape& s, const LayerBuffers& b, in
     a.o_target = s.has_main ? (unsigned)(tiles_h * s.s_o) : 0u;
     a.d_target = s.has_main ? (unsigned)(tiles_h * n_rq) : 0u;
     a.l2_ahead = b.l2_ahead;
+    a.ring_depth = b.ring_depth;       // clamped to the kernel's stage count at launch
     if (s.has_main && (a.n_slices > 8 || s.s_o > 8 || s.hidden % 4)) return RR_ERR_ARG;
     p->grid = grid; p->bn = bn;
     return RR_OK;
@@ -559,7 +563,10 @@ static int launch_layer_bn(const LayerPlan& p, cudaStream_t st) {
     auto kern = decode_layer_tcgen05<BN>;
     static std::atomic<uint64_t> attr_set{0};
     if (ensure_dyn_smem(kern, layer_smem_bytes<BN>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
-    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)layer_smem_bytes<BN>(), st, p.args);
+    LayerArgs args = p.args;
+    constexpr int kStages = GemmCfg<BN>::kStages;
+    if (args.ring_depth < 2 || args.ring_depth > kStages) args.ring_depth = kStages;
+    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)layer_smem_bytes<BN>(), st, args);
     return e == cudaSuccess ? RR_OK : RR_ERR_CUDA;
 }
 int layer_launch(const LayerPlan& p, cudaStream_t st) {
@@ -573,5 +580,6 @@ int layer_launch(const LayerPlan& p, cudaStream_t st) {
 }
 
 void rr_trace_set_layer(unsigned long long* p) { rr_trace_set_local(p); }
+void rr_trace_set_layer_detail(int on) { rr_trace_set_detail_local(on); }
 
 }  // namespace rr

@@ -12,12 +12,13 @@ NAMES = {1: "layer/gemm", 3: "attn_dec", 5: "norm", 8: "embed", 9: "argmax", 12:
          38: "rinv staged", 40: "prod dep O", 41: "prod dep GU", 42: "prod dep DOWN", 43: "prod dep NEXT"}
 spec = SPECS[sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"]
 w = make_weights(spec, seed=0, device="cuda")
-eng = Engine(w, max_batch=64, ctx_max=640, max_prefill_tokens=8192)
+eng = Engine(w, max_batch=64, ctx_max=640, max_prefill_tokens=8192, fuse_layer=True)
 ids = np.random.RandomState(0).randint(0, spec.vocab, size=(64, 512)).astype(np.int32)
 start = np.arange(0, 64 * 512 + 1, 512, dtype=np.int32)
 eng.run_batch(ids.reshape(-1), start, 8)
 N = 40000
 _lib.check(_lib.lib.rr_debug_trace_start(N))
+_lib.check(_lib.lib.rr_debug_trace_detail(1))
 eng.run_batch(ids.reshape(-1), start, 4)
 buf = (C.c_uint64 * (4 * N))(); n = C.c_int32()
 _lib.check(_lib.lib.rr_debug_trace_stop(buf, N, C.byref(n)))
