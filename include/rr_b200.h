@@ -153,10 +153,20 @@ int rr_mt_seed_state(uint64_t seed, uint32_t* out625);
 /* ================================================================================================
  * 2. Prompt token count (K2).  Replaces litellm.token_counter as used for tpm accounting
  *    (no call site in the reference tree; tpm values at reference config.yaml:42).
- *    Counts tokens of the library's byte-level tokenizer: n_tokens = n_utf8_bytes + 1 (BOS). */
+ *    Counts tokens of the library's byte-level tokenizer: n_tokens = n_utf8_bytes + 1 (BOS).
+ *    rr_count_tokens / rr_tokenize are the host forms (one message); the request path uses the batch kernel below. */
 int rr_count_tokens(const uint8_t* text, size_t n_bytes, int32_t* n_tokens);
 int rr_tokenize(const uint8_t* text, size_t n_bytes, int32_t vocab, int32_t* ids, int32_t max_ids,
                 int32_t* n_ids);
+/* The same tokenizer as a CUDA kernel over a batch of messages (csrc/rr_tokenizer.cu): n_texts messages back to back in
+ * `text`, text_off[n_texts + 1] byte offsets.  counts[i] = tokens of message i (what an ADMIT event carries into the tpm
+ * check); ids (optional) = the packed token ids, message i at ids_off[i] = text_off[i] - text_off[0] + i.
+ * rr_tokenize_batch: host buffers (H2D copy, kernel, D2H copies inside; thread-safe).
+ * rr_tokenize_batch_device: device buffers, asynchronous on `stream`; max_text_bytes bounds the longest message. */
+int rr_tokenize_batch(const uint8_t* text, const int64_t* text_off, int n_texts, int32_t vocab, int32_t* counts_out,
+                      int32_t* ids_out, int64_t ids_capacity, int64_t* ids_off_out);
+int rr_tokenize_batch_device(const uint8_t* d_text, const int64_t* d_text_off, int n_texts, int64_t max_text_bytes,
+                             int32_t vocab, int32_t* d_counts, int32_t* d_ids, int64_t* d_ids_off, void* stream);
 
 /* ================================================================================================
  * 3. Kernel-level entry points (used by the parity tests and the engine).

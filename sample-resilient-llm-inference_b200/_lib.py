@@ -135,6 +135,9 @@ PROTOTYPES = {
     "rr_mt_seed_state": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint32)]),
     "rr_count_tokens": (C.c_int, [C.c_char_p, C.c_size_t, c_i32p]),
     "rr_tokenize": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, c_i32p, C.c_int32, c_i32p]),
+    "rr_tokenize_batch": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.c_int32, c_i32p, c_i32p, C.c_int64,
+                                    C.POINTER(C.c_int64)]),
+    "rr_tokenize_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp]),
     "rr_gemm_streamk_planes": (C.c_int, [C.c_int, C.c_int]),
     "rr_gemm_bf16": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                C.c_int, C.c_int, C.c_int, C.c_int, vp]),

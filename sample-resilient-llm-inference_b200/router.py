@@ -103,21 +103,40 @@ class ModelResponse:
                           "total_tokens": self.usage.total_tokens}}
 
 
-# ---------------------------------------------------------------- tokenizer (byte level, in the library)
+# ---------------------------------------------------------------- tokenizer (byte level, CUDA kernel K2 in the library)
+def tokenize_batch(texts: Sequence[str], vocab: int):
+    """Token ids and counts of a batch of messages in ONE launch of the tokenizer kernel (csrc/rr_tokenizer.cu).
+    -> (list of int32 arrays, counts int32[n])."""
+    raw = [t.encode("utf-8") for t in texts]
+    n = len(raw)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in raw], out=off[1:])
+    blob = b"".join(raw)
+    counts = np.zeros(n, dtype=np.int32)
+    ids = np.zeros(int(off[-1]) + n, dtype=np.int32)
+    ids_off = np.zeros(n + 1, dtype=np.int64)
+    _lib.check(_lib.lib.rr_tokenize_batch(blob, off.ctypes.data_as(C.POINTER(C.c_int64)), n, vocab,
+                                          counts.ctypes.data_as(C.POINTER(C.c_int32)), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          len(ids), ids_off.ctypes.data_as(C.POINTER(C.c_int64))), "rr_tokenize_batch")
+    return [ids[ids_off[i]: ids_off[i + 1]] for i in range(n)], counts
+
+
 def tokenize(text: str, vocab: int) -> np.ndarray:
+    return tokenize_batch([text], vocab)[0][0]
+
+
+def count_tokens(text: str) -> int:
+    return int(tokenize_batch([text], 259)[1][0])
+
+
+def tokenize_host(text: str, vocab: int) -> np.ndarray:
+    """Host form of the same tokenizer (rr_tokenize): what the device kernel is checked against."""
     b = text.encode("utf-8")
     ids = np.zeros(len(b) + 1, dtype=np.int32)
     n = C.c_int32()
     _lib.check(_lib.lib.rr_tokenize(b, len(b), vocab, ids.ctypes.data_as(C.POINTER(C.c_int32)),
                                     len(ids), C.byref(n)), "rr_tokenize")
     return ids[: n.value]
-
-
-def count_tokens(text: str) -> int:
-    b = text.encode("utf-8")
-    n = C.c_int32()
-    _lib.check(_lib.lib.rr_count_tokens(b, len(b), C.byref(n)), "rr_count_tokens")
-    return n.value
 
 
 def detokenize(ids: Sequence[int]) -> str:
