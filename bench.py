@@ -304,8 +304,15 @@ def kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak):
                     name, nbytes = "decode_layer_tcgen05 [O + gate/up + down + next QKV]", w_o + w_mlp + w_qkv
                 else:
                     name, nbytes = "decode_layer_tcgen05 [last layer + lm_head]", w_o + w_mlp + w_head
+            elif gemm_total == 3 * L + 1:                       # default path, per layer: QKV GEMM, O GEMM, fused MLP; then lm_head
+                if n_gemm == 3 * L:
+                    name, nbytes = "gemm_bf16_tcgen05<64,1> lm_head", w_head
+                else:
+                    name, nbytes = [("gemm_bf16_tcgen05<64,1> QKV projection (split-K 3)", w_qkv),
+                                    ("gemm_bf16_tcgen05<64,1> O projection (split-K 4)", w_o),
+                                    ("gemm_mlp_tcgen05<64> gate/up + SiLU + down", w_mlp)][n_gemm % 3]
             else:
-                name = "gemm_bf16_tcgen05 / gemm_mlp_tcgen05 (unfused path)"
+                name = "gemm_bf16_tcgen05 (other decode configuration)"
             n_gemm += 1
         r = rows.setdefault(name, {"kernel": name, "launches": 0, "us": 0.0, "bytes": 0})
         r["launches"] += 1; r["us"] += seg_us; r["bytes"] += nbytes
@@ -316,8 +323,10 @@ def kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak):
                     "us_per_step": r["us"], "algorithmic_bytes_per_launch": r["bytes"] // r["launches"],
                     "achieved_gbs": gbs, "frac_of_hbm_peak": (gbs / hbm_peak) if gbs else None})
     out.sort(key=lambda x: -x["us_per_step"])
-    return {"step_us": float((step[-1, 2] - step[0, 2]) / 1e3), "ctx": ctx, "rows": out,
-            "method": "in-kernel %globaltimer stamps of CTA 0 (rr_debug_trace_*), critical-path segments inside the replayed CUDA graph"}
+    return {"step_us_traced": float((step[-1, 2] - step[0, 2]) / 1e3), "ctx": ctx, "rows": out,
+            "method": "in-kernel %globaltimer stamps of CTA 0 (rr_debug_trace_*), critical-path segments inside the replayed CUDA "
+                      "graph; the stamps themselves cost ~3 us per kernel (compare step_us_traced with roofline.ms_per_launch): "
+                      "read the SHARES and the per-kernel fractions as lower bounds"}
 
 
 def per_request_leg(router, model, prompts_np, n_req, M, bursts=2):
@@ -367,13 +376,12 @@ def k1_single_event_latency(router, reps=200):
 
 
 def http_leg(router, model, prompts_np, n_req, M):
-    """64 OpenAI-SDK clients (the reference's client boundary: src/demo_load_balancing.py:24,106-110) streaming from the
-    in-process gateway; TTFT = first SSE chunk."""
+    """n_req OpenAI-SDK clients (the reference's client boundary: src/demo_load_balancing.py:24,106-110) in a SEPARATE
+    process against the in-process gateway (server.py): one non-streamed burst (throughput, latency) and one streamed burst
+    (TTFT = first SSE chunk).  Prompts travel as text: 505 characters -> 512 byte-level tokens."""
     try:
-        import openai
         import uvicorn
         from rr_b200.server import create_app
-        from rr_b200.router import detokenize
     except Exception as e:                                      # noqa: BLE001
         return {"skipped": repr(e)}
     import socket
@@ -384,43 +392,27 @@ def http_leg(router, model, prompts_np, n_req, M):
     t_wait = time.time()
     while not server.started and time.time() - t_wait < 30:
         time.sleep(0.05)
-    # prompts travel as text over HTTP: byte-level tokenizer -> a 511-character message is 512 tokens ("user: " + text + BOS)
-    text = ["".join(chr(97 + int(t) % 26) for t in prompts_np[i][: P_TEXT]) for i in range(n_req)]
-    out, ttft, lat = [None] * n_req, [], []
-    lock = threading.Lock()
-
-    def work(i):
-        client = openai.OpenAI(api_key="demo-key", base_url=f"http://127.0.0.1:{port}", max_retries=0)
-        t0 = time.perf_counter()
-        first, n_chunks = None, 0
-        try:
-            stream = client.chat.completions.create(model=model, messages=[{"role": "user", "content": text[i]}],
-                                                    max_tokens=M, stream=True, timeout=300)
-            for ch in stream:
-                if first is None:
-                    first = time.perf_counter() - t0
-                n_chunks += 1
-            with lock:
-                ttft.append(first); lat.append(time.perf_counter() - t0)
-            out[i] = n_chunks
-        except Exception as e:                                  # noqa: BLE001
-            out[i] = e
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_req)]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    wall = time.perf_counter() - t0
-    server.should_exit = True
-    th.join(timeout=10)
-    errs = [repr(o) for o in out if isinstance(o, Exception)]
-    if not lat:
-        return {"errors": errs[:3]}
-    return {"api": "openai.OpenAI(base_url=http://127.0.0.1:<port>).chat.completions.create(stream=True) x %d threads" % n_req,
-            "value": len(lat) / wall, "unit": "completions/s", "errors": errs[:3],
-            "p50_ttft_ms": float(np.percentile(ttft, 50) * 1e3), "p99_ttft_ms": float(np.percentile(ttft, 99) * 1e3),
-            "p50_latency_ms": float(np.percentile(lat, 50) * 1e3), "prompt_tokens": P_TEXT + 7}
+    out = {"api": "openai.OpenAI(base_url=http://127.0.0.1:<port>).chat.completions.create(...) x %d client threads in a separate "
+                  "process -> server.py -> Router.completion / completion_stream" % n_req, "prompt_tokens": P_TEXT + 7}
+    try:
+        for mode, key in (("0", "non_streamed"), ("1", "streamed")):
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "http_clients.py"), str(port), model, str(n_req),
+                                str(M), str(P_TEXT), mode], capture_output=True, text=True, timeout=600)
+            if p.returncode != 0:
+                out[key] = {"error": p.stderr[-400:]}
+                continue
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            d = {"value": len(r["lat"]) / r["wall_s"] if r["lat"] else None, "unit": "completions/s", "errors": r["errors"],
+                 "p50_latency_ms": float(np.percentile(r["lat"], 50) * 1e3) if r["lat"] else None,
+                 "p99_latency_ms": float(np.percentile(r["lat"], 99) * 1e3) if r["lat"] else None}
+            if r["ttft"]:
+                d["p50_ttft_ms"] = float(np.percentile(r["ttft"], 50) * 1e3)
+                d["p99_ttft_ms"] = float(np.percentile(r["ttft"], 99) * 1e3)
+            out[key] = d
+    finally:
+        server.should_exit = True
+        th.join(timeout=10)
+    return out
 
 
 P_TEXT = 505          # "user: " (6) + 505 characters + BOS = 512 tokens of the byte-level tokenizer
@@ -604,8 +596,8 @@ def main():
             "gpu_launches": int(sm[5].item() + 2 * K),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "decode step = 1 CUDA-graph launch; dominant kernels: decode_layer_tcgen05<64> (weight stream of one "
-                                   "layer + next QKV, 32 launches) and decode_attn_mma_kernel<4> (KV stream, 32 launches)",
+                         "kernel": "decode step = 1 CUDA-graph launch (196 kernels, PDL edges); dominant kernels: gemm_mlp_tcgen05<64> / "
+                                   "gemm_bf16_tcgen05<64,1> (weight streams) and decode_attn_mma_kernel<4> (KV stream); see `kernels`",
                          "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms, "peak_source": peak_src},
             "prefill": {"tflops": pf_tflops, "peak_tflops_sustained": tf_peak, "frac": (pf_tflops / tf_peak) if pf_tflops else None,
                         "ms_per_burst": pf_ms / K, "flops_counted": "executed (last layer's O / MLP and lm_head only on each prompt's last token)",

@@ -184,10 +184,7 @@ enum { RR_OUT_ROWMAJOR_BF16 = 0, RR_OUT_TRANSPOSED_F32 = 1,
 /* D[a,b] = sum_k A[a,k] B[b,k] on tcgen05 tensor cores (bf16 in, fp32 accumulate).
  * mode RR_OUT_ROWMAJOR_BF16:  out bf16 [rowsA, ldo], out[a*ldo + b]         (splits must be 1)
  * mode RR_OUT_TRANSPOSED_F32: out fp32 [splits, ld_rows, ldo], out[(z*ld_rows + b)*ldo + a]
- * bn = tile width along B rows: 16/32/64/128/256.
- * splits == 0 (transposed mode, rowsB <= bn): stream-K — k-block units dealt evenly to all SMs; `out` must
- * hold rr_gemm_streamk_planes(rowsA, K) planes and be zero-initialised once (unwritten planes stay zero). */
-int rr_gemm_streamk_planes(int rowsA, int K);
+ * bn = tile width along B rows: 16/32/64/128/256.  splits >= 1. */
 int rr_gemm_bf16(const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB, int K,
                  void* out, int ldo, int ld_rows, int splits, int mode, int bn, void* stream);
 

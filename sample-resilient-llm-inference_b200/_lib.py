@@ -138,7 +138,6 @@ PROTOTYPES = {
     "rr_tokenize_batch": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.c_int32, c_i32p, c_i32p, C.c_int64,
                                     C.POINTER(C.c_int64)]),
     "rr_tokenize_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int32, vp, vp, vp, vp]),
-    "rr_gemm_streamk_planes": (C.c_int, [C.c_int, C.c_int]),
     "rr_gemm_bf16": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "rr_op_embed": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),

@@ -48,7 +48,6 @@ RR_API const char* rr_last_cuda_error(void) { return g_last_cuda_error; }
 namespace rr {
 void rr_trace_set_gemm(unsigned long long*);
 void rr_trace_set_attn_decode(unsigned long long*);
-void rr_trace_set_attn(unsigned long long*);
 void rr_trace_set_attn_tc(unsigned long long*);
 void rr_trace_set_elementwise(unsigned long long*);
 void rr_trace_set_layer(unsigned long long*);
@@ -67,7 +66,7 @@ RR_API int rr_debug_trace_start(int max_entries) {
     unsigned long long cap = (unsigned long long)max_entries;
     cudaMemcpy(g_trace_dev + 1, &cap, 8, cudaMemcpyHostToDevice);
     g_trace_cap = max_entries;
-    rr_trace_set_gemm(g_trace_dev); rr_trace_set_attn_decode(g_trace_dev); rr_trace_set_attn(g_trace_dev);
+    rr_trace_set_gemm(g_trace_dev); rr_trace_set_attn_decode(g_trace_dev);
     rr_trace_set_attn_tc(g_trace_dev);
     rr_trace_set_elementwise(g_trace_dev); rr_trace_set_layer(g_trace_dev);
     return check_last();
@@ -76,7 +75,7 @@ RR_API int rr_debug_trace_start(int max_entries) {
 RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n) {
     if (!g_trace_dev || !out || !n) return RR_INVALID_ARGUMENT;
     cudaDeviceSynchronize();
-    rr_trace_set_gemm(nullptr); rr_trace_set_attn_decode(nullptr); rr_trace_set_attn(nullptr);
+    rr_trace_set_gemm(nullptr); rr_trace_set_attn_decode(nullptr);
     rr_trace_set_attn_tc(nullptr);
     rr_trace_set_elementwise(nullptr); rr_trace_set_layer(nullptr);
     unsigned long long cnt = 0;
@@ -125,8 +124,6 @@ RR_API int rr_tokenize(const uint8_t* text, size_t n_bytes, int32_t vocab, int32
 }
 
 // ---------------------------------------------------------------- kernels
-RR_API int rr_gemm_streamk_planes(int rowsA, int K) { return gemm_streamk_planes(rowsA, K); }
-
 RR_API int rr_gemm_bf16(const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB, int K,
                         void* out, int ldo, int ld_rows, int splits, int mode, int bn,
                         void* stream) {
@@ -253,8 +250,8 @@ RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_
     a.v_cache = (const __nv_bfloat16*)v_cache; a.out = (__nv_bfloat16*)out; a.seq_start = seq_start;
     a.seq_slot = seq_slot; a.n_seqs = n_seqs; a.max_len = max_len; a.n_heads = n_heads;
     a.n_kv_heads = n_kv_heads; a.ctx_max = ctx_max; a.scale = scale; a.head_dim = 128;
-    if (n_heads / n_kv_heads % 2 == 0 && n_seqs > 0) {
-        // tcgen05 path: the TMA maps need the extents of q and of the caches, which this entry point
+    if (n_seqs > 0) {
+        // the TMA maps need the extents of q and of the caches, which this entry point
         // does not take -- read them back from the caller's index arrays (standalone op, not the engine path).
         std::vector<int32_t> h(n_seqs + 1);
         cudaError_t e = cudaMemcpyAsync(h.data(), seq_slot, sizeof(int32_t) * n_seqs, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
@@ -265,6 +262,7 @@ RR_API int rr_op_prefill_attn(const void* q, const void* k_cache, const void* v_
         for (int i = 0; i < n_seqs; ++i) max_slot = h[i] > max_slot ? h[i] : max_slot;
         (void)prefill_attn_make_maps(&a, h[n_seqs], (long long)(max_slot + 1) * n_kv_heads * ctx_max);
     }
-    launch_prefill_attn(a, (cudaStream_t)stream);
+    const int rcl = launch_prefill_attn(a, (cudaStream_t)stream);
+    if (rcl != RR_OK) return rcl;
     return check_last();
 }

@@ -26,8 +26,9 @@
 // per tile.
 //
 // Work item = (sequence, head pair, 128-row query tile), heaviest (last) query tiles first, strided
-// over the CTAs.  Only even GQA group sizes take this path (the pair must share its kv head); the
-// mma.sync kernel in rr_attn.cu serves the rest (MHA models).
+// over the CTAs.  The two heads of a pair must share their kv head (one K/V ring): even GQA group sizes run pairs;
+// MHA and odd group sizes (Phi-3-mini: 32 heads, 32 kv heads, head_dim 96 zero-padded to 128) run ONE head per item
+// (nh = 1: the second softmax warpgroup and half of the TMEM columns stay idle) on the same tcgen05 / TMA path.
 //
 // Replaces the remote bedrock:InvokeModel call (reference iam/policy.json:8).
 #include "rr_ptx.cuh"
@@ -177,10 +178,11 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem = bars->tmem;
 
-    const int n_pairs = a.n_heads / NH;
+    const int G = a.n_heads / a.n_kv_heads;
+    const int nh = (G % 2 == 0) ? NH : 1;      // query heads per work item: a pair only when both share one kv head
+    const int n_pairs = a.n_heads / nh;
     const int max_qt = (a.max_len + TQ - 1) / TQ;
     const int n_work = max_qt * a.n_seqs * n_pairs;
-    const int G = a.n_heads / a.n_kv_heads;
 
     griddep_wait();
     trace_dep(tr_slot);
@@ -196,11 +198,11 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 const WorkFetch f = nf;
                 fetch_work(a, w + gridDim.x, n_work, n_pairs, true, nf);
                 if (!decode_work(a, w, n_pairs, max_qt, f, k)) continue;
-                const int head0 = k.pair * NH, kvh = head0 / G;
+                const int head0 = k.pair * nh, kvh = head0 / G;
                 const int kv_row0 = (f.slot * a.n_kv_heads + kvh) * a.ctx_max;
                 mbar_wait(&bars->q_empty, (q_it & 1) ^ 1);
-                mbar_arrive_expect_tx(&bars->q_full, NH * Q_BYTES);
-                for (int h = 0; h < NH; ++h)
+                mbar_arrive_expect_tx(&bars->q_full, nh * Q_BYTES);
+                for (int h = 0; h < nh; ++h)
                     for (int c = 0; c < 2; ++c)
                         tma_load_2d(smem + OFF_Q + h * Q_BYTES + c * 16384, &tmQ, &bars->q_full,
                                     (head0 + h) * 128 + c * 64, k.tok0 + k.qt * TQ);
@@ -226,7 +228,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             // have finished reading for the previous item (o_free).
             auto pv = [&](uint32_t kvit_t, uint32_t sit_t, bool first) {
                 const uint32_t v_u = kv_u + (kvit_t % NS) * 2 * KV_BYTES + KV_BYTES, b = sit_t & 1;
-                for (int h = 0; h < NH; ++h) {
+                for (int h = 0; h < nh; ++h) {
                     mbar_wait(&bars->p_full[h][b], (sit_t >> 1) & 1);
                     if (first) mbar_wait(&bars->o_free[h], (item_it & 1) ^ 1);
                     tcgen05_fence_after();
@@ -252,7 +254,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     mbar_wait(&bars->kv_full[s], (kv_it / NS) & 1);
                     tcgen05_fence_after();
                     const uint32_t k_u = kv_u + s * 2 * KV_BYTES;
-                    for (int h = 0; h < NH; ++h) {
+                    for (int h = 0; h < nh; ++h) {
                         // S(j) lands on the columns of S(j-2) / P(j-2): PV(j-2) was issued before, the pipe runs in order
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
@@ -268,7 +270,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 ++item_it;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && ((warp - 4) >> 2) < nh) {
         // ------------------------------------------------------------------ softmax + output
         const int h = (warp - 4) >> 2, quarter = warp & 3, row = quarter * 32 + lane;
         const uint32_t t_base = tmem + ((uint32_t)(quarter * 32) << 16) + h * 256;
@@ -282,7 +284,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const WorkFetch f = nf;
             fetch_work(a, w + gridDim.x, n_work, n_pairs, false, nf);
             if (!decode_work(a, w, n_pairs, max_qt, f, k)) continue;
-            const int head = k.pair * NH + h;
+            const int head = k.pair * nh + h;
             const int qi = k.qt * TQ + row;                       // query index inside the sequence
             const int last_key = qi < k.len ? qi : k.len - 1;     // causal / ragged bound (inclusive)
             float m_ref = -INFINITY, l = 0.f;                     // reference maximum (log2 domain), row sum
@@ -411,12 +413,9 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 }  // namespace
 
-int g_use_attn_tc = -1;
-
 bool prefill_attn_tc_eligible(const PrefillAttnArgs& a) {
-    if (g_use_attn_tc < 0) g_use_attn_tc = std::getenv("RR_NO_ATTN_TC") ? 0 : 1;
     const int G = a.n_kv_heads > 0 ? a.n_heads / a.n_kv_heads : 0;
-    return g_use_attn_tc && a.has_maps && G >= 2 && G % 2 == 0 && a.ctx_max % TKV == 0 && a.head_dim % 8 == 0;
+    return a.has_maps && G >= 1 && a.n_heads % a.n_kv_heads == 0 && a.ctx_max % TKV == 0 && a.head_dim % 8 == 0;
 }
 
 // q: [q_rows, n_heads*128]; caches: [kv_rows = n_slots*n_kv_heads*ctx_max, 128].  Boxes: Q 64 x 128 rows,
@@ -437,11 +436,20 @@ int prefill_attn_make_maps(PrefillAttnArgs* a, long long q_rows, long long kv_ro
 int launch_prefill_attn_tc(const PrefillAttnArgs& a, cudaStream_t st) {
     static std::atomic<uint64_t> attr{0};
     if (ensure_dyn_smem(prefill_attn_tc_kernel, (int)TC_SMEM, attr) != cudaSuccess) return RR_ERR_CUDA;
-    const int n_work = ((a.max_len + TQ - 1) / TQ) * a.n_seqs * (a.n_heads / NH);
+    const int nh = ((a.n_heads / a.n_kv_heads) % 2 == 0) ? NH : 1;
+    const int n_work = ((a.max_len + TQ - 1) / TQ) * a.n_seqs * (a.n_heads / nh);
     const int grid = n_work < num_sms() ? n_work : num_sms();
     cudaError_t e = launch_pdl(prefill_attn_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TC_SMEM, st,
                                a.tmQ, a.tmK, a.tmV, a);
     return e == cudaSuccess ? RR_OK : RR_ERR_CUDA;
+}
+
+// The one prefill attention path.  (Round 1 kept an mma.sync kernel for MHA models and as an A/B switch; the tcgen05 kernel
+// now serves every group size, so there is nothing to fall back to: an ineligible call fails.)
+int launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st) {
+    if (a.n_seqs <= 0 || a.max_len <= 0) return RR_OK;
+    if (!prefill_attn_tc_eligible(a)) return RR_ERR_ARG;
+    return launch_prefill_attn_tc(a, st);
 }
 
 void rr_trace_set_attn_tc(unsigned long long* p) { rr_trace_set_local(p); }

@@ -115,7 +115,7 @@ struct rr_engine {
     int32_t *d_tok, *d_pos, *d_slot;
     float* x;
     __nv_bfloat16 *xn, *qbuf, *attn_out, *act;
-    float *part_qkv, *part_o, *part_gu, *part_down, *logits, *attn_ws;   // stream-K partial planes (zeroed once)
+    float *part_qkv, *part_o, *part_gu, *part_down, *logits, *attn_ws;   // split-K partial planes
     float2* rope_table;
     __nv_bfloat16 *kcache, *vcache;
     size_t kv_layer_stride;
@@ -430,7 +430,7 @@ static int run_prefill(rr_engine* e, const int32_t* ids, const int32_t* seq_star
         pa.q = e->pq; pa.k_cache = kc; pa.v_cache = vc; pa.out = e->pattn; pa.seq_start = p_ss; pa.seq_slot = p_sl;
         pa.n_seqs = n_seqs; pa.max_len = max_len; pa.n_heads = d.n_heads; pa.n_kv_heads = d.n_kv_heads;
         pa.ctx_max = e->o.ctx_max; pa.scale = 1.0f / sqrtf((float)d.head_dim); pa.head_dim = d.head_dim;
-        launch_prefill_attn(pa, s); ++nl;
+        if (launch_prefill_attn(pa, s) != RR_OK) return RR_CUDA_ERROR; ++nl;
         if (l + 1 == d.n_layers) {
             // ---- trimmed tail: n_seqs rows through O, MLP, final norm (decode-orientation kernels, decode buffers)
             const int B = e->Bm;
@@ -652,8 +652,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     TRYC(cudaEventCreate(&e->ev0));
     TRYC(cudaEventCreate(&e->ev1));
     const int B = e->Bm;
-    // Uniform split-K planes.  (stream-K — gemm_plan_init(splits = 0) — was measured on B200: it only helps
-    // gate/up by 5 % and costs extra planes for the consumers: 4.55 -> 4.92 ms per decode step.)
+    // Uniform split-K planes.
     e->s_qkv = pick_splits(e->nqkv, d.hidden); e->s_o = pick_splits(d.hidden, e->nq);
     e->s_gu = pick_splits(2 * d.inter, d.hidden); e->s_down = pick_splits(d.hidden, d.inter);
     e->fuse_silu = (w->flags & RR_WEIGHTS_WGU_INTERLEAVED64) && e->s_gu == 1 && e->bn_dec >= 32 &&
@@ -720,8 +719,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
             pa.q = e->pq; pa.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
             pa.v_cache = e->vcache + (size_t)l * e->kv_layer_stride; pa.n_heads = d.n_heads;
             pa.n_kv_heads = d.n_kv_heads; pa.ctx_max = opts->ctx_max; pa.head_dim = d.head_dim;
-            if (d.n_heads / d.n_kv_heads % 2 == 0 && opts->ctx_max % 64 == 0)
-                TRY(prefill_attn_make_maps(&pa, T, (long long)B * d.n_kv_heads * opts->ctx_max));
+            TRY(prefill_attn_make_maps(&pa, T, (long long)B * d.n_kv_heads * opts->ctx_max));   // ctx_max % 64 == 0 (checked above)
         }
         DecodeAttnArgs& da = e->attn_args[l];
         da.q = e->qbuf; da.k_cache = e->kcache + (size_t)l * e->kv_layer_stride;
@@ -828,19 +826,9 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
         TRYC(cudaMemcpy(e->mlp_items, sched.data(), sched.size() * sizeof(MlpItem), cudaMemcpyHostToDevice));
         TRY(dalloc(e, &e->mlp_ready, 8));
         e->mlp.resize(L);
-        // experiment knob: RR_KV_PREFETCH_TILES = n -> the MLP kernel of layer l prefetches the first n K/V tiles per
-        // (row, kv head) of layer l + 1's attention into L2
-        const int pf_tiles = getenv("RR_KV_PREFETCH_TILES") ? atoi(getenv("RR_KV_PREFETCH_TILES")) : 0;
         for (int l = 0; l < L; ++l) {
             TRY(mlp_plan_init(&e->mlp[l], e->wgu[l], e->wdown[l], d.inter, d.hidden, e->xn, B, e->act, e->part_down, B,
                               e->bn_dec, e->mlp_items, max_items, grid, e->mlp_ready, e->mlp_slice_kb));
-            if (pf_tiles > 0) {
-                const int ln = (l + 1) % L;                      // the last layer warms layer 0 of the next step
-                KvPrefetch& pf = e->mlp[l].args.pf;
-                pf.k = e->kcache + (size_t)ln * e->kv_layer_stride; pf.v = e->vcache + (size_t)ln * e->kv_layer_stride;
-                pf.slot = e->d_slot; pf.pos = e->d_pos; pf.rows = B; pf.n_kv_heads = d.n_kv_heads; pf.ctx_max = opts->ctx_max;
-                pf.tiles = pf_tiles;
-            }
         }
     }
     TRYC(cudaDeviceSynchronize());

@@ -10,12 +10,8 @@
 //   * decode   (OUT_TRANSPOSED_F32): A = weight [N, K] (UMMA M side, streamed once from HBM),
 //                                    B = activations [batch<=BN, K]; fp32 partial planes
 //                                    P[z][b][n] reduced by the consumer kernel (rr_elementwise.cu).
-//     Work split for decode: either uniform split-K (splits planes), or stream-K (splits == 0):
-//     the tilesA x kblocks k-block units are dealt out to the CTAs as equal contiguous ranges that
-//     ignore tile boundaries, so all 148 SMs stream exactly the same number of weight bytes
-//     (no wave quantisation: 224 gate/up tiles on 148 SMs would otherwise run at 76 %).
-//     A tile cut by c CTA boundaries is written to planes 0..c; the schedule is static, so planes
-//     that are never written stay zero in a dedicated, once-zeroed partial buffer.
+//     Work split for decode: uniform split-K (splits planes); the wave-quantisation tail of the big gate/up
+//     projection is removed by the fused MLP kernel below (per-slice dataflow), not by a stream-K split.
 //
 // PDL: the weight operand is constant, its first pipeline stages are requested before
 // griddepcontrol.wait; only the activation operand and the output wait for the preceding kernel.
@@ -378,11 +374,6 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
     }
 }
 
-#ifndef RR_L2_AHEAD
-#define RR_L2_AHEAD 0
-#endif
-constexpr int kL2Ahead = RR_L2_AHEAD;   // experiment knob (k-blocks of 16 KB per CTA prefetched to L2 before the PDL wait)
-
 template <int BN, int MODE, int CAP = 8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -447,8 +438,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t phase = 0;
             bool have = sched.next(t);
             // PDL prefetch of the constant (weight) operand for the first `pre` k-blocks.
-            // (An additional L2 prefetch of the rest of the panel was measured SLOWER on B200:
-            //  5.12 -> 5.37 ms per decode step.)
+            // (An additional L2 prefetch of the panel behind the ring was measured in round 1: whole panel 5.12 -> 5.37 ms
+            //  per decode step, bounded to 8 / 16 k-blocks no gain / slower; removed.)
             int pre = 0;
             if (have) {
                 pre = min(kStages, t.kb1 - t.kb0);
@@ -461,11 +452,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tma_load_2d_hint(smemB + i * Cfg::kStageBytesB, &tmB, &full_bar[i], (t.kb0 + i) * BLOCK_K,
                                          t.b_tile * BN, polB);
                 }
-            }
-            if (decode_orient<MODE>() && have && kL2Ahead > 0) {
-                // bounded L2 look-ahead: the next kL2Ahead weight k-blocks of this CTA's panel (beyond the smem ring)
-                const int kb_lim = min(t.kb1, t.kb0 + pre + kL2Ahead);
-                for (int kb = t.kb0 + pre; kb < kb_lim; ++kb) tma_prefetch_l2_2d(&tmA, kb * BLOCK_K, t.a_tile * BLOCK_A);
             }
             griddep_wait();
             trace_dep(tr_slot);
@@ -702,25 +688,6 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         RopeEpi no_rope;
         no_rope.q_out = nullptr; no_rope.k_cache = nullptr; no_rope.v_cache = nullptr; no_rope.slot = nullptr;
         no_rope.pos = nullptr; no_rope.table = nullptr; no_rope.n_heads = 0; no_rope.n_kv_heads = 0; no_rope.ctx_max = 0;
-        if (a.pf.k != nullptr) {
-            // These warps idle until the first accumulator is ready: use them to pull the first K/V tiles of the next
-            // attention kernel into L2 (one 16 KB piece per thread) while this kernel streams weights with evict_first.
-            const int per = 2 * a.pf.tiles;
-            const int id = (int)blockIdx.x * 128 + etid;
-            if (id < a.pf.rows * a.pf.n_kv_heads * per) {
-                const int rk = id / per, u = id - rk * per;
-                const int row = rk / a.pf.n_kv_heads, kvh = rk - row * a.pf.n_kv_heads;
-                const int slot = a.pf.slot[row];
-                const int tile = u >> 1;
-                const int ctx = slot >= 0 ? a.pf.pos[row] + 1 : 0;
-                const int n_tok = min(64, ctx - tile * 64);
-                if (n_tok > 0) {
-                    const __nv_bfloat16* base = (u & 1) ? a.pf.v : a.pf.k;
-                    const __nv_bfloat16* src = base + (((size_t)slot * a.pf.n_kv_heads + kvh) * a.pf.ctx_max + (size_t)tile * 64) * 128;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n_tok * 256) : "memory");
-                }
-            }
-        }
         griddep_wait();
         for (int it = 0; get(it, t, ph); ++it) {
             const int acc = it & 1;
@@ -1005,70 +972,34 @@ int num_sms() {                         // of the current device (one process ma
     return n;
 }
 
-// stream-K geometry: number of CTAs and of partial planes for [rowsA, K] weights.
-int gemm_streamk_ctas(int rowsA, int K) {
-    const long long U = (long long)((rowsA + BLOCK_A - 1) / BLOCK_A) * ((K + BLOCK_K - 1) / BLOCK_K);
-    return (int)(U < num_sms() ? U : num_sms());
-}
-int gemm_streamk_planes(int rowsA, int K) {
-    const int tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A, kb = (K + BLOCK_K - 1) / BLOCK_K;
-    const long long U = (long long)tilesA * kb;
-    const long long n = gemm_streamk_ctas(rowsA, K);
-    auto c_of = [&](long long x) { return (int)(((x + 1) * n + U - 1) / U) - 1; };
-    int planes = 1;
-    for (int T = 0; T < tilesA; ++T) {
-        const int p = c_of((long long)T * kb + kb - 1) - c_of((long long)T * kb) + 1;
-        if (p > planes) planes = p;
-    }
-    return planes;
-}
-
-// Experiment knob: a 7-stage ring (173 KB) at BN = 64 lets one decode-attention CTA (52 KB) be co-resident with the QKV
-// GEMM and start under PDL.  Measured on one box, A/B: QKV GEMM 15.6 -> 17.3 us, attention unchanged (32.7 us),
-// step +1.5 % -- the early CTAs only compete for bandwidth.  Default stays 8.
-#ifndef RR_DEC_RING_CAP
-#define RR_DEC_RING_CAP 8
-#endif
 template <int BN, int MODE>
 static int launch_one(const GemmPlan& p, cudaStream_t st) {
-    constexpr int CAP = (MODE == OUT_TRANSPOSED_F32 && BN == 64) ? RR_DEC_RING_CAP : 8;
+    constexpr int CAP = 8;
     auto kern = gemm_bf16_tcgen05<BN, MODE, CAP>;
     static std::atomic<uint64_t> attr_set{0};
     if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, MODE, CAP>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
-    int grid;
-    if (p.streamk) {
-        grid = gemm_streamk_ctas(p.rowsA, p.K);
-    } else {
-        const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
-        const int tilesB = (p.rowsB + BN - 1) / BN;
-        const int n_work = tilesA * tilesB * p.splits;
-        grid = n_work < num_sms() ? n_work : num_sms();
-    }
+    const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
+    const int tilesB = (p.rowsB + BN - 1) / BN;
+    const int n_work = tilesA * tilesB * p.splits;
+    const int grid = n_work < num_sms() ? n_work : num_sms();
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, MODE, CAP>(), st, p.tmA, p.tmB,
-                                p.out, p.rowsA, p.rowsB, p.K, p.streamk ? 0 : p.splits, p.ldo, p.ld_rows, p.rope);
+                                p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows, p.rope);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
 static bool decode_orient_rt(int mode) { return mode == OUT_TRANSPOSED_F32 || mode == OUT_TRANSPOSED_SILU; }
 
-// splits >= 1: uniform split-K with `splits` planes.  splits == 0: stream-K (decode orientation, rowsB <= bn);
-// p->splits then holds the number of planes the consumer must sum (gemm_streamk_planes).
+// splits >= 1: uniform split-K with `splits` planes.
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn) {
     if (K % 8 != 0 || ldA % 8 != 0 || ldB % 8 != 0) return RR_ERR_ARG;
     if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256)) return RR_ERR_ARG;
     const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
-    p->streamk = 0;
-    if (splits == 0) {
-        if (mode != OUT_TRANSPOSED_F32 || rowsB > bn) return RR_ERR_ARG;
-        p->streamk = 1;
-        splits = gemm_streamk_planes(rowsA, K);
-    }
-    if (splits < 1) splits = 1;
+    if (splits < 1) return RR_ERR_ARG;
     if (splits > kblocks) splits = kblocks;
     if (mode == OUT_ROWMAJOR_BF16 && (splits != 1 || ldo % 8 != 0)) return RR_ERR_ARG;
     // fused SiLU*mul epilogues: weights row-interleaved in 64-row gate/up blocks, one plane, bf16 act output
-    if (mode == OUT_TRANSPOSED_SILU && (splits != 1 || p->streamk || bn < 32 || rowsA % 128 != 0)) return RR_ERR_ARG;
+    if (mode == OUT_TRANSPOSED_SILU && (splits != 1 || bn < 32 || rowsA % 128 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_SILU && (splits != 1 || bn != 256 || rowsB % 128 != 0 || ldo % 8 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_ROPE && (splits != 1 || bn != 256 || rowsB % 128 != 0)) return RR_ERR_ARG;
     if (mode == OUT_ROWMAJOR_RESID && (splits != 1 || bn < 32 || ldo % 4 != 0)) return RR_ERR_ARG;
@@ -1186,7 +1117,6 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
     if (rc != RR_OK) return rc;
     a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
     a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
-    memset(&a.pf, 0, sizeof(a.pf));
     p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
     return RR_OK;
 }

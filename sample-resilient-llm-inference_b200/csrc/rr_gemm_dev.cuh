@@ -13,7 +13,7 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int GROUP_A = 16;    // raster group: 16 A tiles share the streamed B tiles through L2
 
-// CAP bounds the smem ring (experiment knob RR_DEC_RING_CAP in rr_gemm.cu).
+// CAP bounds the smem ring.
 template <int BN, int CAP = 8>
 struct GemmCfg {
     static constexpr int kStageBytesA = BLOCK_A * BLOCK_K * 2;
@@ -40,43 +40,21 @@ struct WorkItem {
     int a_tile, b_tile, z, kb0, kb1;
 };
 
-// Deterministic per-CTA sequence of work items; every warp role walks the same sequence.
+// Deterministic per-CTA sequence of work items (uniform split-K); every warp role walks the same sequence.
+// (A stream-K split -- k-block units dealt evenly to the SMs regardless of tile boundaries -- was measured in round 1:
+// 4.55 -> 4.92 ms per decode step, the consumers read more planes than the better balance returns; removed.)
 struct WorkSched {
     int tilesA, tilesB, splits, kblocks, n_work, w;
-    long long cur, u_end, U;
-    int streamk;
 
     __device__ __forceinline__ void init(int rowsA, int rowsB, int K, int splits_, int BN) {
         tilesA = (rowsA + BLOCK_A - 1) / BLOCK_A;
         tilesB = (rowsB + BN - 1) / BN;
         kblocks = (K + BLOCK_K - 1) / BLOCK_K;
-        streamk = splits_ == 0;
         splits = splits_;
-        if (streamk) {
-            U = (long long)tilesA * kblocks;
-            cur = (U * blockIdx.x) / gridDim.x;
-            u_end = (U * (blockIdx.x + 1)) / gridDim.x;
-        } else {
-            n_work = tilesA * tilesB * splits;
-            w = blockIdx.x;
-        }
+        n_work = tilesA * tilesB * splits;
+        w = blockIdx.x;
     }
     __device__ __forceinline__ bool next(WorkItem& it) {
-        if (streamk) {
-            if (cur >= u_end) return false;
-            const int T = (int)(cur / kblocks);
-            const long long tile_u0 = (long long)T * kblocks;
-            it.a_tile = T;
-            it.b_tile = 0;
-            it.kb0 = (int)(cur - tile_u0);
-            const long long left = u_end - cur;
-            it.kb1 = (kblocks - it.kb0 < left) ? kblocks : it.kb0 + (int)left;
-            // plane = number of CTA range boundaries inside this tile before `cur`
-            const int c_first = (int)(((tile_u0 + 1) * gridDim.x + U - 1) / U) - 1;
-            it.z = (int)blockIdx.x - c_first;
-            cur += it.kb1 - it.kb0;
-            return true;
-        }
         if (w >= n_work) return false;
         it.z = w % splits;
         const int q = w / splits;

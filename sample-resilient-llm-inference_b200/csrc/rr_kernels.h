@@ -47,7 +47,7 @@ struct RopeEpi {
 struct GemmPlan {
     CUtensorMap tmA, tmB;
     void* out;
-    int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas, streamk;
+    int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas;
     RopeEpi rope;             // OUT_ROWMAJOR_ROPE only
     CUtensorMap tmB2;         // 2-CTA kernel: B with a 128-row box (each CTA of the pair stages half of the 256 rows)
     int two_cta;
@@ -63,8 +63,6 @@ void engine_set_done_hook(rr_engine* e, EngineDoneHook fn, void* ctx);
 int engine_limits(const rr_engine* e, int* ctx_max, int* max_prefill, int* vocab);
 int router_shape(const rr_router* r, int* n_deployments, int* n_groups);
 int router_dep_replica(const rr_router* r, int deployment);
-int gemm_streamk_planes(int rowsA, int K);
-int gemm_streamk_ctas(int rowsA, int K);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows);
 int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B, int rowsB, int ldB,
                    int K, void* out, int ldo, int ld_rows, int splits, int mode, int bn);
@@ -79,16 +77,6 @@ struct MlpItem {             // 16 bytes, read as int4
     int kb0, kb1;             // k-block range
     int z;                    // down: output plane = K-slice index (also the index into `ready`)
 };
-// L2 prefetch of the NEXT attention kernel's first K/V tiles, issued by the idle epilogue warps at the start of the
-// fused MLP kernel (earlier tokens' K/V rows are constant within a step, see rr_attn_decode.cu).
-struct KvPrefetch {
-    const __nv_bfloat16* k;   // next layer's K cache [slot][kv_head][ctx_max][128]; nullptr: off
-    const __nv_bfloat16* v;
-    const int32_t* slot;      // [rows]
-    const int32_t* pos;       // [rows]
-    int rows, n_kv_heads, ctx_max;
-    int tiles;                // 64-token tiles per (row, kv head) to prefetch, K and V each
-};
 struct MlpArgs {
     CUtensorMap tmA0, tmB0;   // gate/up: weights [2*inter, hidden] (64-row interleaved), activations xn [rows, hidden]
     CUtensorMap tmA1, tmB1;   // down: weights [hidden, inter], activations act [rows, inter]
@@ -99,7 +87,6 @@ struct MlpArgs {
     int max_items;
     unsigned* ready;          // [n_slices], zero at launch
     int slice_kb;
-    KvPrefetch pf;
 };
 struct MlpPlan {
     MlpArgs args;
@@ -207,7 +194,7 @@ void launch_rope_table(float2* table, int ctx_max, float theta, int head_dim, cu
 void launch_argmax(PartIn logits, int rows, int vocab, int32_t* out_tok, float* out_val,
                    const int32_t* row_active, int32_t* pos_inc, cudaStream_t st);
 
-// ---- attention (rr_attn.cu) ---------------------------------------------------------------------
+// ---- attention (rr_attn_decode.cu, rr_attn_tc.cu) ---------------------------------------------------
 struct DecodeAttnArgs {
     const __nv_bfloat16* q;   // [rows, n_heads*128]
     const __nv_bfloat16* k_cache;
@@ -242,11 +229,11 @@ struct PrefillAttnArgs {
     int n_seqs, max_len, n_heads, n_kv_heads, ctx_max;
     float scale;
     int head_dim;             // true head dim: `out` head stride; q / caches padded to 128
-    int has_maps = 0;         // tmQ/tmK/tmV valid (prefill_attn_make_maps): enables the tcgen05 kernel
+    int has_maps = 0;         // tmQ/tmK/tmV valid (prefill_attn_make_maps): required
     CUtensorMap tmQ, tmK, tmV;
 };
-void launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st);
-// tcgen05 path (rr_attn_tc.cu): even GQA group sizes only; launch_prefill_attn dispatches to it.
+int launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t st);   // RR_ERR_ARG when the maps are missing / shape unsupported
+// tcgen05 kernel (rr_attn_tc.cu): head pairs for even GQA group sizes, one head per item otherwise (MHA).
 int prefill_attn_make_maps(PrefillAttnArgs* a, long long q_rows, long long kv_rows);
 bool prefill_attn_tc_eligible(const PrefillAttnArgs& a);
 int launch_prefill_attn_tc(const PrefillAttnArgs& a, cudaStream_t st);

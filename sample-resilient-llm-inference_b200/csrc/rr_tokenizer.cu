@@ -90,32 +90,48 @@ struct TokScratch {                      // per-process staging (grown on demand
     size_t cap_bytes = 0, cap_texts = 0;
 };
 static TokScratch g_tok;
+// forget the buffers of another device (they stay allocated there: a process normally tokenizes on one device)
+static TokScratch& TokScratchReset(TokScratch& s) {
+    s.stream = nullptr;
+    s.h_text = s.d_text = nullptr; s.h_off = s.d_off = s.d_ids_off = s.h_ids_off = nullptr;
+    s.d_counts = s.h_counts = s.d_ids = s.h_ids = nullptr;
+    s.cap_bytes = s.cap_texts = 0;
+    return s;
+}
 
 static int tok_reserve(TokScratch& s, size_t bytes, size_t n) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (s.device != dev) {                                       // first use (or the caller switched devices): start over
-        s.device = dev; s.cap_bytes = s.cap_texts = 0; s.stream = nullptr;
+        TokScratchReset(s);
+        s.device = dev;
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return RR_CUDA_ERROR;
     }
-    if (bytes > s.cap_bytes) {
-        const size_t c = bytes * 2 + 4096;
-        if (s.h_text) { cudaFreeHost(s.h_text); cudaFree(s.d_text); cudaFree(s.d_ids); cudaFreeHost(s.h_ids); }
-        if (cudaMallocHost(&s.h_text, c) != cudaSuccess || cudaMalloc(&s.d_text, c) != cudaSuccess) return RR_CUDA_ERROR;
-        s.cap_bytes = c;
-    }
-    if (n > s.cap_texts || !s.d_ids) {
-        const size_t c = n > s.cap_texts ? n * 2 + 64 : s.cap_texts;
-        if (s.h_off) { cudaFreeHost(s.h_off); cudaFree(s.d_off); cudaFree(s.d_ids_off); cudaFree(s.d_counts); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_ids_off); }
-        if (cudaMallocHost(&s.h_off, (c + 1) * 8) != cudaSuccess || cudaMalloc(&s.d_off, (c + 1) * 8) != cudaSuccess ||
-            cudaMalloc(&s.d_ids_off, (c + 1) * 8) != cudaSuccess || cudaMalloc(&s.d_counts, c * 4) != cudaSuccess ||
-            cudaMallocHost(&s.h_counts, c * 4) != cudaSuccess || cudaMallocHost(&s.h_ids_off, (c + 1) * 8) != cudaSuccess)
-            return RR_CUDA_ERROR;
-        s.cap_texts = c;
-        if (s.d_ids) { cudaFree(s.d_ids); cudaFreeHost(s.h_ids); }
-        const size_t ni = s.cap_bytes + s.cap_texts + 16;
-        if (cudaMalloc(&s.d_ids, ni * 4) != cudaSuccess || cudaMallocHost(&s.h_ids, ni * 4) != cudaSuccess) return RR_CUDA_ERROR;
-    }
+    if (bytes <= s.cap_bytes && n <= s.cap_texts) return RR_OK;
+    // grow: free everything, allocate for the new capacities (the scratch is only ever used under s.mu, synchronously)
+    const size_t cb = bytes > s.cap_bytes ? bytes * 2 + 4096 : s.cap_bytes;
+    const size_t ct = n > s.cap_texts ? n * 2 + 64 : s.cap_texts;
+    if (s.h_text) cudaFreeHost(s.h_text);
+    if (s.d_text) cudaFree(s.d_text);
+    if (s.h_off) cudaFreeHost(s.h_off);
+    if (s.d_off) cudaFree(s.d_off);
+    if (s.d_ids_off) cudaFree(s.d_ids_off);
+    if (s.d_counts) cudaFree(s.d_counts);
+    if (s.h_counts) cudaFreeHost(s.h_counts);
+    if (s.h_ids_off) cudaFreeHost(s.h_ids_off);
+    if (s.d_ids) cudaFree(s.d_ids);
+    if (s.h_ids) cudaFreeHost(s.h_ids);
+    s.h_text = s.d_text = nullptr; s.h_off = s.d_off = s.d_ids_off = s.h_ids_off = nullptr;
+    s.d_counts = s.h_counts = s.d_ids = s.h_ids = nullptr;
+    s.cap_bytes = s.cap_texts = 0;
+    const size_t ni = cb + ct + 16;
+    if (cudaMallocHost(&s.h_text, cb) != cudaSuccess || cudaMalloc(&s.d_text, cb) != cudaSuccess ||
+        cudaMallocHost(&s.h_off, (ct + 1) * 8) != cudaSuccess || cudaMalloc(&s.d_off, (ct + 1) * 8) != cudaSuccess ||
+        cudaMalloc(&s.d_ids_off, (ct + 1) * 8) != cudaSuccess || cudaMalloc(&s.d_counts, ct * 4) != cudaSuccess ||
+        cudaMallocHost(&s.h_counts, ct * 4) != cudaSuccess || cudaMallocHost(&s.h_ids_off, (ct + 1) * 8) != cudaSuccess ||
+        cudaMalloc(&s.d_ids, ni * 4) != cudaSuccess || cudaMallocHost(&s.h_ids, ni * 4) != cudaSuccess)
+        return RR_CUDA_ERROR;
+    s.cap_bytes = cb; s.cap_texts = ct;
     return RR_OK;
 }
 

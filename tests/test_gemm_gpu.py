@@ -76,29 +76,6 @@ def test_gemm_exact_small_integers():
     assert torch.equal(got, ref)
 
 
-@pytest.mark.parametrize("rowsA,rowsB,K,bn", [(6144, 64, 4096, 64), (4096, 64, 14336, 64), (28672, 48, 4096, 64),
-                                              (4096, 64, 4096, 64), (1000, 7, 320, 16), (128, 16, 64, 16),
-                                              (128256, 64, 4096, 64), (512, 8, 512, 16)])
-def test_gemm_streamk(rowsA, rowsB, K, bn):
-    """stream-K: equal contiguous k-block ranges per SM; planes never written must stay zero."""
-    from rr_b200 import _lib
-    g = torch.Generator(device="cuda").manual_seed(rowsA + K)
-    A = (torch.randn(rowsA, K, device="cuda", generator=g) * 0.05).bfloat16()
-    B = torch.randn(rowsB, K, device="cuda", generator=g).bfloat16()
-    planes = _lib.lib.rr_gemm_streamk_planes(rowsA, K)
-    assert 1 <= planes <= 64
-    out = torch.zeros(planes, rowsB, rowsA, device="cuda", dtype=torch.float32)
-    for rep in range(2):          # static schedule: a second launch overwrites the same (tile, plane) set
-        rc = _lib.lib.rr_gemm_bf16(A.data_ptr(), rowsA, K, B.data_ptr(), rowsB, K, K, out.data_ptr(), rowsA, rowsB,
-                                   0, 1, bn, None)
-        _lib.check(rc, "rr_gemm_bf16 stream-K")
-        torch.cuda.synchronize()
-        got = out.sum(0)
-        ref = B.float() @ A.float().t()
-        err = (got - ref).abs().max().item()
-        assert torch.isfinite(got).all() and err <= 1e-3 * ref.abs().max().item() + 1e-4, (rep, err)
-
-
 def _interleave64(w, inter):
     g, u = w[:inter].view(-1, 64, w.shape[1]), w[inter:].view(-1, 64, w.shape[1])
     return torch.stack([g, u], 1).reshape(2 * inter, w.shape[1]).contiguous()

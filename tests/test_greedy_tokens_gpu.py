@@ -3,9 +3,10 @@ decode of the same prompts".  The engine decodes FREE-RUNNING (its own tokens fe
 the tokens of the real transformers LlamaForCausalLM.generate(do_sample=False) on the same weights, in fp32 and in bf16.
 
 Seeded random weights give almost flat logits (top-2 margin ~0.2 sigma over a 128 k vocabulary) where bf16 rounding noise
-alone flips an argmax every few tokens, so the weights are SHARPENED first: lm_head row perm[t] =
-embedding row t (a fixed random permutation), which makes the model predict perm[current token] with a top-2 margin of tens of
-logit standard deviations while every layer still runs at its real shape and contributes to the hidden state.  The margin
+alone flips an argmax every few tokens, so the weights are SHARPENED first: unit-variance embedding
+rows and lm_head row perm[t] = embedding row t (a fixed random permutation), which makes the model predict perm[current
+token] with a top-2 margin of several logit standard deviations while every layer still runs at its real shape and
+contributes a comparable share of the hidden state.  The margin
 is measured and asserted to exceed 10x the stated logit tolerance of tests/test_engine_gpu.py, so an exact match is a
 meaningful statement about the whole pipeline (prefill, KV cache positions, RoPE, decode under the CUDA graph at 64 active
 rows -- the configuration bench.py times) and not luck.  Small numeric deviations are covered by the teacher-forced logit
@@ -18,8 +19,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _sharpen(w, seed=0):
+    """Embedding rows scaled to unit variance per element (so the token embedding is a large part of the residual stream
+    next to the layer outputs, which are O(1) per element after RMSNorm-ed inputs), lm_head row perm[t] = embedding row t."""
     g = torch.Generator(device=w.embed.device).manual_seed(seed)
     perm = torch.randperm(w.spec.vocab, generator=g, device=w.embed.device)
+    w.embed.copy_((w.embed.float() / w.embed.float().std()).bfloat16())
     w.lm_head.index_copy_(0, perm, w.embed)
     return perm
 

@@ -14,7 +14,7 @@ def time_gemm(rowsA, rowsB, K, mode, bn, splits, iters=20, ncopies=4):
     if mode == 0:
         out = torch.empty(rowsA, rowsB, device="cuda", dtype=torch.bfloat16); ldo, ldr = rowsB, 0
     else:
-        planes = splits if splits > 0 else lib.rr_gemm_streamk_planes(rowsA, K)
+        planes = splits
         out = torch.zeros(planes, rowsB, rowsA, device="cuda", dtype=torch.float32); ldo, ldr = rowsA, rowsB
     def run(i):
         A = As[i % ncopies]
@@ -32,9 +32,9 @@ def time_gemm(rowsA, rowsB, K, mode, bn, splits, iters=20, ncopies=4):
 
 if __name__ == "__main__":
     print("decode orientation (weights streamed): rowsA=N_out rowsB=batch")
-    for name, N, K, splits_list in [("qkv", 6144, 4096, [3, 0]), ("o", 4096, 4096, [4, 0]),
-                                    ("gate_up", 28672, 4096, [1, 0]), ("down", 4096, 14336, [4, 0]),
-                                    ("lm_head", 128256, 4096, [1, 0])]:
+    for name, N, K, splits_list in [("qkv", 6144, 4096, [3]), ("o", 4096, 4096, [4]),
+                                    ("gate_up", 28672, 4096, [1]), ("down", 4096, 14336, [4]),
+                                    ("lm_head", 128256, 4096, [1])]:
         for s in splits_list:
             for bn in (64,):
                 ms = time_gemm(N, 64, K, 1, bn, s, ncopies=max(2, int(300e6 / (N * K * 2)) + 1))
