@@ -11,7 +11,9 @@ import openai
 
 def main():
     port, model, n, max_new, n_chars, stream = int(sys.argv[1]), sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6] == "1"
-    texts = ["".join(chr(97 + (i * 7 + j * 13) % 26) for j in range(n_chars)) for i in range(n)]
+    start_at = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0          # wall-clock time at which every client process fires
+    first_id = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+    texts = ["".join(chr(97 + ((first_id + i) * 7 + j * 13) % 26) for j in range(n_chars)) for i in range(n)]
     lat, ttft, errs = [None] * n, [None] * n, []
     barrier = threading.Barrier(n + 1)
 
@@ -37,12 +39,15 @@ def main():
     ths = [threading.Thread(target=work, args=(i,)) for i in range(n)]
     for t in ths:
         t.start()
+    d = start_at - time.time()
+    if d > 0:
+        time.sleep(d)
     barrier.wait()
     t0 = time.perf_counter()
     for t in ths:
         t.join()
     wall = time.perf_counter() - t0
-    print(json.dumps({"wall_s": wall, "lat": [x for x in lat if x is not None], "ttft": [x for x in ttft if x is not None],
+    print(json.dumps({"wall_s": wall, "t_end": time.time(), "lat": [x for x in lat if x is not None], "ttft": [x for x in ttft if x is not None],
                       "errors": errs[:3]}))
 
 

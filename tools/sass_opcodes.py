@@ -12,7 +12,7 @@ for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
         kern = m.group(1); hist[kern] = collections.Counter(); continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
     if m and kern:
         op, mods = m.group(1), m.group(2)
         hist[kern][op] += 1
