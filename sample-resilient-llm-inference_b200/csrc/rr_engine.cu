@@ -654,12 +654,6 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     const int B = e->Bm;
     // Uniform split-K planes.
     e->s_qkv = pick_splits(e->nqkv, d.hidden); e->s_o = pick_splits(d.hidden, e->nq);
-    const bool half_ring = getenv("RR_HALF_RING") && e->bn_dec == 64;      // experiment: QKV / O GEMMs with 2 CTAs per SM
-    if (half_ring) {
-        const int kq = (d.hidden + 63) / 64, ko = (e->nq + 63) / 64;
-        if (kq / (2 * e->s_qkv) >= 8 && 2 * e->s_qkv <= 8) e->s_qkv *= 2;
-        if (ko / (2 * e->s_o) >= 8 && 2 * e->s_o <= 8) e->s_o *= 2;
-    }
     e->s_gu = pick_splits(2 * d.inter, d.hidden); e->s_down = pick_splits(d.hidden, d.inter);
     e->fuse_silu = (w->flags & RR_WEIGHTS_WGU_INTERLEAVED64) && e->s_gu == 1 && e->bn_dec >= 32 &&
                    (2 * d.inter) % 128 == 0;
@@ -740,7 +734,6 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
                            e->nqkv, B, e->s_qkv, OUT_TRANSPOSED_F32, e->bn_dec));
         TRY(gemm_plan_init(&e->pl_o[l], e->wo[l], d.hidden, e->nq, e->attn_out, B, e->nq, e->nq, e->part_o, d.hidden,
                            B, e->s_o, OUT_TRANSPOSED_F32, e->bn_dec));
-        e->pl_qkv[l].half_ring = e->pl_o[l].half_ring = half_ring ? 1 : 0;
         if (e->fuse_silu)
             TRY(gemm_plan_init(&e->pl_gu[l], e->wgu[l], 2 * d.inter, d.hidden, e->xn, B, d.hidden, d.hidden, e->act,
                                d.inter, B, 1, OUT_TRANSPOSED_SILU, e->bn_dec));
@@ -827,8 +820,7 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     }
     if (e->fuse_mlp) {
         std::vector<MlpItem> sched;
-        const bool mlp_half = getenv("RR_HALF_RING") && atoi(getenv("RR_HALF_RING")) >= 2 && e->bn_dec == 64;   // experiment
-        const int grid = (mlp_half ? 2 : 1) * num_sms();
+        const int grid = num_sms();
         const int max_items = mlp_schedule(grid, d.inter, d.hidden, e->mlp_slice_kb, &sched);
         TRY(dalloc(e, &e->mlp_items, sched.size()));
         TRYC(cudaMemcpy(e->mlp_items, sched.data(), sched.size() * sizeof(MlpItem), cudaMemcpyHostToDevice));

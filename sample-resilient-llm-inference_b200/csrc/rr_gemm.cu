@@ -29,7 +29,7 @@ namespace rr {
 
 // Epilogue of one work item: TMEM accumulator (this warp's 32 lanes x BN columns at taddr0) -> global memory, in the
 // layout / fusion selected by MODE.  Shared by the 1-CTA kernel, the 2-CTA kernel and (by copy) the chain kernel.
-template <int BN, int MODE, bool SILU_SINGLE_BUF = false>
+template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const WorkItem& t, int quarter, int lane,
                                               void* __restrict__ out, int rowsA, int rowsB, int ldo, int ld_rows,
                                               const RopeEpi& rope, float* silu_stage) {
@@ -55,7 +55,7 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
         __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(out);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
-            float* buf = SILU_SINGLE_BUF ? stage : stage + ((c >> 5) & 1) * (32 * 64);
+            float* buf = stage + ((c >> 5) & 1) * (32 * 64);
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr0 + c, v);
             tmem_ld_wait();
@@ -73,7 +73,6 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
                         act[(size_t)b * ldo + n] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
                 }
             }
-            if (SILU_SINGLE_BUF) asm volatile("bar.sync 2, 128;" ::: "memory");   // the one buffer is rewritten by the next chunk
         }
     } else if constexpr (MODE == OUT_ROWMAJOR_ROPE) {
         // 256 columns = two 128-wide heads of the fused qkv projection; thread = token row.
@@ -375,10 +374,8 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
     }
 }
 
-// CAP <= 4: half ring (96 KB at BN = 64), two CTAs per SM -- the next kernel's CTAs can become resident (prologue, weight
-// prefetch) while a CTA of this kernel still streams; launched with up to 2 CTAs per SM (experiment RR_HALF_RING).
 template <int BN, int MODE, int CAP = 8>
-__global__ void __launch_bounds__(GEMM_THREADS, (CAP <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   void* __restrict__ out, int rowsA, int rowsB, int K, int splits, int ldo,
                   int ld_rows, const RopeEpi rope) {
@@ -566,10 +563,10 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     return v;
 }
 
-template <int BN, int CAP = 8>
-__global__ void __launch_bounds__(GEMM_THREADS, (CAP <= 4 ? 2 : 1))
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
-    using Cfg = GemmCfg<BN, CAP>;
+    using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -699,8 +696,8 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             if (ph == 0)
-                epilogue_item<BN, OUT_TRANSPOSED_SILU, (CAP <= 4)>(taddr0, a_row, t, quarter, lane, a.act, 2 * a.inter, a.rows, a.inter, 0,
-                                                                   no_rope, silu_stage);
+                epilogue_item<BN, OUT_TRANSPOSED_SILU>(taddr0, a_row, t, quarter, lane, a.act, 2 * a.inter, a.rows, a.inter, 0,
+                                                       no_rope, silu_stage);
             else
                 epilogue_item<BN, OUT_TRANSPOSED_F32>(taddr0, a_row, t, quarter, lane, a.out1, a.hidden, a.rows, a.hidden,
                                                       a.ld_rows, no_rope, nullptr);
@@ -975,19 +972,16 @@ int num_sms() {                         // of the current device (one process ma
     return n;
 }
 
-template <int BN, int MODE, int CAP = 8>
+template <int BN, int MODE>
 static int launch_one(const GemmPlan& p, cudaStream_t st) {
-    if constexpr (CAP == 8 && BN == 64 && MODE == OUT_TRANSPOSED_F32) {
-        if (p.half_ring) return launch_one<BN, MODE, 4>(p, st);
-    }
+    constexpr int CAP = 8;
     auto kern = gemm_bf16_tcgen05<BN, MODE, CAP>;
     static std::atomic<uint64_t> attr_set{0};
     if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, MODE, CAP>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
     const int tilesA = (p.rowsA + BLOCK_A - 1) / BLOCK_A;
     const int tilesB = (p.rowsB + BN - 1) / BN;
     const int n_work = tilesA * tilesB * p.splits;
-    const int max_ctas = (CAP <= 4 ? 2 : 1) * num_sms();
-    const int grid = n_work < max_ctas ? n_work : max_ctas;
+    const int grid = n_work < num_sms() ? n_work : num_sms();
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, MODE, CAP>(), st, p.tmA, p.tmB,
                                 p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows, p.rope);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
@@ -1012,7 +1006,7 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     if (mode < 0 || mode > OUT_ROWMAJOR_RESID) return RR_ERR_ARG;
     memset(&p->rope, 0, sizeof(p->rope));
     p->rowsA = rowsA; p->rowsB = rowsB; p->K = K; p->out = out; p->ldo = ldo; p->ld_rows = ld_rows;
-    p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0; p->half_ring = 0;
+    p->splits = splits; p->mode = mode; p->bn = bn; p->max_ctas = 0;
     int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
     if (rc != RR_OK) return rc;
     // prefill orientation with 256-wide tiles and at least one full 256-row pair: 2-CTA kernel (B box = 128 rows)
@@ -1114,7 +1108,7 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
                   unsigned* ready, int slice_kb) {
     if (!p || !Wgu || !Wd || !xn || !act || !planes || !items_dev || !ready) return RR_ERR_ARG;
     if (inter % 64 || (2 * inter) % BLOCK_A || hidden % 8 || rows > bn || bn < 32 || slice_kb < 1) return RR_ERR_ARG;
-    if ((2 * inter) / BLOCK_A > 0xffff || grid < 1 || grid > 2 * num_sms()) return RR_ERR_ARG;
+    if ((2 * inter) / BLOCK_A > 0xffff || grid < 1 || grid > num_sms()) return RR_ERR_ARG;
     MlpArgs& a = p->args;
     int rc = make_tmap_bf16_2d(&a.tmA0, Wgu, 2 * inter, hidden, hidden, BLOCK_A);
     if (rc == RR_OK) rc = make_tmap_bf16_2d(&a.tmB0, xn, rows, hidden, hidden, bn);
@@ -1123,25 +1117,23 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
     if (rc != RR_OK) return rc;
     a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
     a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
-    p->half_ring = grid > num_sms() ? 1 : 0;          // more CTAs than SMs: the 4-stage, two-CTAs-per-SM instance (bn = 64)
-    if (p->half_ring && bn != 64) return RR_ERR_ARG;
     p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
     return RR_OK;
 }
 
-template <int BN, int CAP = 8>
+template <int BN>
 static int launch_mlp_bn(const MlpPlan& p, cudaStream_t st) {
-    auto kern = gemm_mlp_tcgen05<BN, CAP>;
+    auto kern = gemm_mlp_tcgen05<BN>;
     static std::atomic<uint64_t> attr_set{0};
-    if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU, CAP>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
-    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU, CAP>(), st, p.args);
+    if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
+    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), st, p.args);
     return e == cudaSuccess ? RR_OK : RR_ERR_CUDA;
 }
 // Requires all CTAs co-resident (grid <= SM count; one CTA per SM by shared memory) and ready[] zero at launch.
 int mlp_launch(const MlpPlan& p, cudaStream_t st) {
     switch (p.bn) {
         case 32: return launch_mlp_bn<32>(p, st);
-        case 64: return p.half_ring ? launch_mlp_bn<64, 4>(p, st) : launch_mlp_bn<64>(p, st);
+        case 64: return launch_mlp_bn<64>(p, st);
         case 128: return launch_mlp_bn<128>(p, st);
         case 256: return launch_mlp_bn<256>(p, st);
     }

@@ -24,8 +24,7 @@ struct GemmCfg {
     static constexpr uint32_t kTmemCols =
         (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    // OUT_TRANSPOSED_SILU: up-row exchange, [32 cols][64 rows] fp32, double-buffered (single buffer in the half-ring variant)
-    static constexpr int kSiluStageBytes = (CAP <= 4 ? 1 : 2) * 32 * 64 * 4;
+    static constexpr int kSiluStageBytes = 2 * 32 * 64 * 4;   // OUT_TRANSPOSED_SILU: up-row exchange, 2 x [32 cols][64 rows] fp32
 };
 template <int MODE>
 __host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }

@@ -48,7 +48,6 @@ struct GemmPlan {
     CUtensorMap tmA, tmB;
     void* out;
     int rowsA, rowsB, K, splits, ldo, ld_rows, mode, bn, max_ctas;
-    int half_ring;            // decode orientation, bn = 64: 4-stage ring, two CTAs per SM (experiment)
     RopeEpi rope;             // OUT_ROWMAJOR_ROPE only
     CUtensorMap tmB2;         // 2-CTA kernel: B with a 128-row box (each CTA of the pair stages half of the 256 rows)
     int two_cta;
@@ -91,7 +90,7 @@ struct MlpArgs {
 };
 struct MlpPlan {
     MlpArgs args;
-    int grid, bn, n_slices, half_ring;
+    int grid, bn, n_slices;
 };
 // Host schedule: `items` gets grid * max_items entries (CTA-major); returns max_items.
 int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items);
