@@ -9,13 +9,16 @@ from rr_b200.engine import Engine
 
 var = sys.argv[1]
 val = sys.argv[2] if len(sys.argv) > 2 else "1"
+extra = dict(kv.split("=") for kv in sys.argv[3:])          # further VAR=VALUE pairs set together with the first one
 spec = SPECS["llama-3-8b"]
 w = make_weights(spec, seed=0, device="cuda")
 os.environ.pop(var, None)
 eng_a = Engine(w, max_batch=64, ctx_max=640, max_prefill_tokens=8192)
 os.environ[var] = val
+os.environ.update(extra)
 eng_b = Engine(w, max_batch=64, ctx_max=640, max_prefill_tokens=8192)
 os.environ.pop(var, None)
+for k in extra: os.environ.pop(k, None)
 ids = np.random.RandomState(0).randint(0, spec.vocab, size=(64, 512)).astype(np.int32)
 start = np.arange(0, 64 * 512 + 1, 512, dtype=np.int32)
 def run(e, new=48):
@@ -28,10 +31,10 @@ os.environ[var] = val
 run(eng_b, 8)
 os.environ.pop(var, None)
 ta, tb = [], []
-for _ in range(4):
+for _ in range(int(os.environ.get("AB_REPS", "4"))):
     a, toks_a = run(eng_a); b, toks_b = run(eng_b)
     ta.append(a); tb.append(b)
 print(f"A (default)    : {sorted(ta)[len(ta)//2]:.4f} ms/step median  {['%.3f' % t for t in ta]}")
-print(f"B ({var}={val}): {sorted(tb)[len(tb)//2]:.4f} ms/step median  {['%.3f' % t for t in tb]}")
+print(f"B ({var}={val} {extra if extra else ''}): {sorted(tb)[len(tb)//2]:.4f} ms/step median  {['%.3f' % t for t in tb]}")
 print("tokens equal:", toks_a == toks_b)
 eng_a.close(); eng_b.close()
