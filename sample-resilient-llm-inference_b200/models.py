@@ -91,6 +91,7 @@ class Weights:
     wdown: List[torch.Tensor] = field(default_factory=list)
     norm_attn: List[torch.Tensor] = field(default_factory=list)
     norm_mlp: List[torch.Tensor] = field(default_factory=list)
+    flat: Optional[torch.Tensor] = None      # the one allocation every tensor above is a view of (make_weights); None after .to()
 
     def tensors(self) -> List[torch.Tensor]:
         out = [self.embed, self.lm_head, self.final_norm]
@@ -119,11 +120,28 @@ def make_weights(spec: ModelSpec, seed: int = 0, sigma: float = 0.02, device="cu
     """
     dev = torch.device(device)
     g = torch.Generator(device=dev).manual_seed(seed)
+    nq, nkv = spec.n_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
+    # ONE flat allocation, every tensor a 256-byte-aligned view of it: the start-up weight broadcast is then a single
+    # ncclBroadcast instead of 195 small ones (broadcast_weights)
+    shapes = [(spec.vocab, spec.hidden), (spec.vocab, spec.hidden), (spec.hidden,)]
+    for _ in range(spec.n_layers):
+        shapes += [(nq + 2 * nkv, spec.hidden), (spec.hidden, nq), (2 * spec.inter, spec.hidden), (spec.hidden, spec.inter),
+                   (spec.hidden,), (spec.hidden,)]
+    offs, total = [], 0
+    for sh in shapes:
+        n = 1
+        for d in sh:
+            n *= d
+        offs.append(total)
+        total += (n + 127) // 128 * 128
+    flat = torch.empty(total, device=dev, dtype=torch.bfloat16)
+    views = iter([flat[o: o + torch.Size(sh).numel()].view(*sh) for o, sh in zip(offs, shapes)])
 
     def rnd(*shape):
+        out = next(views)
+        assert tuple(out.shape) == tuple(shape)
         if allocate_only:
-            return torch.empty(*shape, device=dev, dtype=torch.bfloat16)
-        out = torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+            return out
         rows = shape[0]
         step = max(1, (1 << 26) // max(1, shape[1]))      # bound the fp32 temporary to 256 MB
         for r0 in range(0, rows, step):
@@ -132,14 +150,15 @@ def make_weights(spec: ModelSpec, seed: int = 0, sigma: float = 0.02, device="cu
         return out
 
     def norm():
+        out = next(views)
         if allocate_only:
-            return torch.empty(spec.hidden, device=dev, dtype=torch.bfloat16)
+            return out
         w = torch.ones(spec.hidden, device=dev)
         if norm_jitter:
             w = w + norm_jitter * torch.randn(spec.hidden, device=dev, generator=g)
-        return w.bfloat16()
+        out.copy_(w.bfloat16())
+        return out
 
-    nq, nkv = spec.n_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
     w = Weights(spec, rnd(spec.vocab, spec.hidden), rnd(spec.vocab, spec.hidden), norm())
     for _ in range(spec.n_layers):
         w.wqkv.append(rnd(nq + 2 * nkv, spec.hidden))
@@ -148,12 +167,18 @@ def make_weights(spec: ModelSpec, seed: int = 0, sigma: float = 0.02, device="cu
         w.wdown.append(rnd(spec.hidden, spec.inter))
         w.norm_attn.append(norm())
         w.norm_mlp.append(norm())
+    w.flat = flat
     return w
 
 
 def broadcast_weights(w: Weights, src: int = 0, group=None) -> None:
     """Start-up weight broadcast (K12): rank `src` -> every replica of the model group over
-    NCCL/NVLink.  The only collective on the path; requests never cross GPUs afterwards."""
+    NCCL/NVLink.  The only collective on the path; requests never cross GPUs afterwards.
+    Weights made by make_weights live in one flat buffer: ONE ncclBroadcast of 16 GB (round 1 issued 195 per-tensor calls
+    and reached ~70 % of the link rate)."""
     import torch.distributed as dist
+    if w.flat is not None:
+        dist.broadcast(w.flat, src=src, group=group)
+        return
     for t in w.tensors():
         dist.broadcast(t, src=src, group=group)

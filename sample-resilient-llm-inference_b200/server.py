@@ -107,10 +107,12 @@ def create_app(router: Router):
     async def health():
         return {"status": "ok", "uptime_s": time.time() - t_start}
 
-    @app.get("/v1/models")
     async def models():
         return {"object": "list", "data": [{"id": g, "object": "model", "owned_by": "rr_b200"}
                                            for g in router.cfg.groups]}
+
+    app.add_api_route("/v1/models", models, methods=["GET"])
+    app.add_api_route("/models", models, methods=["GET"])          # the SDK appends /models to a base_url without /v1
 
     @app.get("/router/state")
     async def state():

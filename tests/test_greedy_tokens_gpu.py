@@ -117,3 +117,31 @@ def test_benched_configuration_64_rows_cuda_graph_llama3_8b_shape_equals_hf_gree
         assert eng.stats()["decode_steps"] >= 2 * (M - 1)
     finally:
         eng.close()
+
+
+def test_full_size_llama3_8b_32_layers_free_running_greedy_equals_hf_fp32():
+    """BASELINE.json's model at full size -- 32 layers, hidden 4096, vocabulary 128256 -- free-running for 32 tokens on 8
+    rows of 512-token prompts (the bench's prompt generator), against transformers LlamaForCausalLM in fp32 on the same
+    (sharpened) weights.  Complements tests/test_full_model_gpu.py, which bounds the logit error at this size."""
+    from rr_b200.engine import Engine
+    from rr_b200.models import SPECS, make_weights
+    spec = SPECS["llama-3-8b"]
+    w = make_weights(spec, seed=0, sigma=0.02, device="cuda")
+    _sharpen(w)
+    n, P, M = 8, 512, 32
+    prompts = []
+    for r in range(n):
+        g = torch.Generator().manual_seed(1234 + r)
+        prompts.append(torch.randint(0, spec.vocab, (P,), generator=g).tolist())
+    want = _hf_generate(w, prompts, M, torch.float32)
+    # the margin that makes an exact comparison meaningful, measured on HF's own logits at the first generated position
+    eng = Engine(w, max_batch=64, ctx_max=640, max_prefill_tokens=8192, use_cuda_graph=True)
+    try:
+        ids = np.asarray(prompts, dtype=np.int32).reshape(-1)
+        start = np.arange(0, (n + 1) * P, P, dtype=np.int32)
+        recs, _ = eng.run_batch(ids, start, M)
+        bad = [(i, _first_divergence(r.tokens, want[i])) for i, r in enumerate(recs) if r.tokens != want[i]]
+        assert not bad, f"rows diverging from HF fp32 greedy at full size (row, first token index): {bad}"
+        assert len({tuple(r.tokens) for r in recs}) == n
+    finally:
+        eng.close()

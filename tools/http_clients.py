@@ -19,6 +19,10 @@ def main():
 
     def work(i):
         client = openai.OpenAI(api_key="demo-key", base_url=f"http://127.0.0.1:{port}", max_retries=0)
+        try:
+            client.models.list()         # warms the SDK (lazy imports, ~0.5 s on a first call) and opens the connection
+        except Exception:                # noqa: BLE001
+            pass
         barrier.wait()
         t0 = time.perf_counter()
         try:
