@@ -511,7 +511,12 @@ def main():
             start = np.arange(0, (len(mine) + 1) * P, P, dtype=np.int32)
             recs, _ = eng.run_batch(ids, start, M) if len(mine) else ([], None)
             assert all(r.status == 0 and len(r.tokens) == M for r in recs)
-            token_sums.append(hash(tuple(tuple(r.tokens) for r in recs)) & 0xFFFFFFFFFFFF)
+            # checksum keyed by REQUEST (which rank serves a request may change from burst to burst: least-busy ties are
+            # broken through the router's RNG stream), summed over the ranks
+            chk = sum((hash((int(i), tuple(r.tokens))) & 0xFFFFFFFFFF) for i, r in zip(mine, recs))
+            ct = torch.tensor([chk], dtype=torch.int64, device=torch.device("cuda", local))
+            dist.all_reduce(ct, op=dist.ReduceOp.SUM)
+            token_sums.append(int(ct.item()))
             if collect:
                 ttfts.extend(r.ttft for r in recs); lat.extend(r.latency for r in recs)
             parallel.gather_done(len(mine), world, rank, device=torch.device("cuda", local))
@@ -541,8 +546,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     st = eng.stats()
     dev_s = (st["prefill_ms_total"] + st["decode_ms_total"]) / 1e3
-    # identical prompts every step and deterministic kernels: every step must have generated exactly the same tokens
-    # (the assignment of requests to ranks is deterministic too)
+    # identical prompts every step and deterministic kernels: every step must have generated exactly the same tokens for
+    # every request
     assert len(set(token_sums)) == 1, "generated tokens differ between bursts"
 
     # ---- max over ranks
