@@ -130,32 +130,38 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             float2 klo = make_float2(0.f, 0.f), khi = klo, v0 = klo, v1 = klo;
 #pragma unroll
             for (int h = 0; h < G; ++h) lo[h] = hi[h] = make_float2(0.f, 0.f);
-            for (int z = 0; z < a.qkv.n_splits; ++z) {
-                const float* pl = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)z * a.qkv.split_stride +
-                                  (size_t)row * a.qkv.ld;
-                const float2 z2 = make_float2(0.f, 0.f);
-                float2 tl[G], th[G];
+            // The split-K planes are summed here.  All loads of up to kPlaneBatch planes are issued before the first add: with
+            // one plane per loop iteration the prologue was n_splits dependent L2 round trips (~1.3 us each under load): a
+            // no-split QKV experiment (one plane) showed 4 us of the kernel's 34 were exactly that.  In-process A/B on the
+            // split-K path: 4.376 vs 4.493 ms per decode step (profiles/r02_layer_kernel_experiment.md).
+            constexpr int kPlaneBatch = G <= 2 ? 4 : (G <= 4 ? 3 : 2);
+            const float2 z2 = make_float2(0.f, 0.f);
+            const int pstep = kPlaneBatch;
+            for (int zb = 0; zb < a.qkv.n_splits; zb += pstep) {
+                float2 tl[kPlaneBatch][G], th[kPlaneBatch][G], tk[kPlaneBatch][4];
 #pragma unroll
-                for (int h = 0; h < G; ++h) {
-                    tl[h] = lane_on ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + i) : z2;
-                    th[h] = lane_on ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + half + i) : z2;
-                }
-                float2 t0 = z2, t1 = z2, t2 = z2, t3 = z2;
-                if (owns_new) {
-                    if (lane_on) {
-                        t0 = *reinterpret_cast<const float2*>(pl + kcol + i);
-                        t1 = *reinterpret_cast<const float2*>(pl + kcol + half + i);
+                for (int zz = 0; zz < kPlaneBatch; ++zz) {
+                    const bool on = zb + zz < a.qkv.n_splits;
+                    const float* pl = reinterpret_cast<const float*>(a.qkv.ptr) + (size_t)(on ? zb + zz : 0) * a.qkv.split_stride +
+                                      (size_t)row * a.qkv.ld;
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        tl[zz][h] = (on && lane_on) ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + i) : z2;
+                        th[zz][h] = (on && lane_on) ? *reinterpret_cast<const float2*>(pl + (kvh * G + h) * hd + half + i) : z2;
                     }
-                    if (v_on) {
-                        t2 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane);
-                        t3 = *reinterpret_cast<const float2*>(pl + vcol + 4 * lane + 2);
-                    }
+                    tk[zz][0] = (on && owns_new && lane_on) ? *reinterpret_cast<const float2*>(pl + kcol + i) : z2;
+                    tk[zz][1] = (on && owns_new && lane_on) ? *reinterpret_cast<const float2*>(pl + kcol + half + i) : z2;
+                    tk[zz][2] = (on && owns_new && v_on) ? *reinterpret_cast<const float2*>(pl + vcol + 4 * lane) : z2;
+                    tk[zz][3] = (on && owns_new && v_on) ? *reinterpret_cast<const float2*>(pl + vcol + 4 * lane + 2) : z2;
                 }
 #pragma unroll
-                for (int h = 0; h < G; ++h) { lo[h].x += tl[h].x; lo[h].y += tl[h].y; hi[h].x += th[h].x; hi[h].y += th[h].y; }
-                if (owns_new) {
-                    klo.x += t0.x; klo.y += t0.y; khi.x += t1.x; khi.y += t1.y;
-                    v0.x += t2.x; v0.y += t2.y; v1.x += t3.x; v1.y += t3.y;
+                for (int zz = 0; zz < kPlaneBatch; ++zz) {            // plane order = the summation order of the unbatched loop
+#pragma unroll
+                    for (int h = 0; h < G; ++h) {
+                        lo[h].x += tl[zz][h].x; lo[h].y += tl[zz][h].y; hi[h].x += th[zz][h].x; hi[h].y += th[zz][h].y;
+                    }
+                    klo.x += tk[zz][0].x; klo.y += tk[zz][0].y; khi.x += tk[zz][1].x; khi.y += tk[zz][1].y;
+                    v0.x += tk[zz][2].x; v0.y += tk[zz][2].y; v1.x += tk[zz][3].x; v1.y += tk[zz][3].y;
                 }
             }
             // smem rows are 128 wide: zero the padding beyond the true head dim first
