@@ -52,9 +52,11 @@ void rr_trace_set_attn_tc(unsigned long long*);
 void rr_trace_set_elementwise(unsigned long long*);
 void rr_trace_set_layer(unsigned long long*);
 void rr_trace_set_layer_detail(int);
+void rr_trace_set_gemm_detail(int);
 }
 static unsigned long long* g_trace_dev = nullptr;
 static int g_trace_cap = 0;
+static int g_trace_detail_on = 0;
 
 // Debug timeline: (kernel id, start ns, dependency-resolved ns, end ns) of CTA 0 of every library kernel (globaltimer).
 RR_API int rr_debug_trace_start(int max_entries) {
@@ -81,6 +83,7 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
     unsigned long long cnt = 0;
     cudaMemcpy(&cnt, g_trace_dev, 8, cudaMemcpyDeviceToHost);
     int m = (int)(cnt < (unsigned long long)g_trace_cap ? cnt : g_trace_cap);
+    if (g_trace_detail_on) m = g_trace_cap;       // fixed-slot detail marks live at the end of the buffer; empty rows are zero
     if (m > max_entries) m = max_entries;
     cudaMemcpy(out, g_trace_dev + 2, (size_t)m * 32, cudaMemcpyDeviceToHost);
     *n = m;
@@ -91,7 +94,9 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
 
 // Per-item marks of sample CTAs inside the persistent layer kernel (tools/trace_layer.py); off by default.
 RR_API int rr_debug_trace_detail(int on) {
+    g_trace_detail_on = on ? 1 : 0;
     rr_trace_set_layer_detail(on ? 1 : 0);
+    rr_trace_set_gemm_detail(on ? 1 : 0);
     return check_last();
 }
 

@@ -58,7 +58,7 @@ template <int G>
 __global__ void __launch_bounds__(DEC_THREADS, 4)
 decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     extern __shared__ uint8_t dsm_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = align_smem_1024(dsm_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + RING * UNIT_BYTES);
     uint64_t* empty_bar = full_bar + RING;
     uint64_t* newkv_bar = empty_bar + RING;

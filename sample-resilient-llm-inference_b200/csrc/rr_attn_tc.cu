@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const PrefillAttnArgs a) {
     extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = align_smem_1024(tc_smem_raw);
     Bars* bars = reinterpret_cast<Bars*>(smem + OFF_BAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 

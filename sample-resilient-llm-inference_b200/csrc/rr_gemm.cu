@@ -374,17 +374,88 @@ __device__ __forceinline__ void epilogue_item(uint32_t taddr0, int a_row, const 
     }
 }
 
+// ---- TMA-store epilogues (decode orientation, BN <= 64) ---------------------------------------------------------------------
+// Under a saturated weight stream an LSU store costs the issuing warp 75-170 ns (tools/trace_mlp.py: 64 four-byte stores
+// per thread = 5 us per planes tile, the 2-byte act stores of the SiLU epilogue + the fence = 14 us from "accumulator
+// ready" to "tile published", and the down items of the fused MLP kernel wait exactly for that).  Here the 128 epilogue
+// threads transpose the tile through shared memory and ONE thread hands it to the TMA engine as a single bulk store.
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 4, 128;" ::: "memory"); }
+
+// planes tile: stage[b][n] fp32, b < BN, n < 128 (n = accumulator row = this thread)  ->  P[z][b][a_tile * 128 + n]
+template <int BN>
+__device__ __forceinline__ void epilogue_planes_tma(uint32_t taddr0, const WorkItem& t, int quarter, int lane, int etid,
+                                                    const CUtensorMap* tmOut, float* stage) {
+    constexpr int CH = (BN >= 32) ? 32 : 16;
+    if (etid == 0) bulk_wait_read0();              // the previous item's store has read the staging tile
+    epi_bar();
+    float* col = stage + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+        uint32_t v[32];
+        if constexpr (CH == 32) {
+            tmem_ld_32x32b_x32(taddr0 + c, v);
+        } else {
+            uint32_t v16[16];
+            tmem_ld_32x32b_x16(taddr0 + c, v16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v16[j];
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH; ++j) col[(c + j) * 128] = __uint_as_float(v[j]);      // lanes = consecutive n: conflict-free
+    }
+    fence_proxy_async();                           // generic-proxy smem writes -> the TMA engine's reads
+    epi_bar();
+    if (etid == 0) {
+        tma_store_3d(tmOut, stage, t.a_tile * BLOCK_A, t.b_tile * BN, t.z);
+        bulk_commit();
+    }
+}
+
+// SiLU tile of the gate/up projection: lanes 0..63 of the accumulator = gate rows, 64..127 = the matching up rows (exchanged
+// through `exch`); act_stage[b][n64] bf16  ->  act[b][a_tile * 64 + n64]
+template <int BN>
+__device__ __forceinline__ void epilogue_silu_tma(uint32_t taddr0, const WorkItem& t, int quarter, int lane, int etid,
+                                                  const CUtensorMap* tmAct, float* exch, __nv_bfloat16* act_stage) {
+    const bool is_up = quarter >= 2;
+    const int r64 = (quarter & 1) * 32 + lane;
+    if (etid == 0) bulk_wait_read0();
+    epi_bar();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        float* buf = exch + ((c >> 5) & 1) * (32 * 64);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr0 + c, v);
+        tmem_ld_wait();
+        if (is_up) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (!is_up) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                act_stage[(c + j) * 64 + r64] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
+        }
+    }
+    fence_proxy_async();
+    epi_bar();
+    if (etid == 0) {
+        tma_store_2d(tmAct, act_stage, t.a_tile * 64, t.b_tile * BN);
+        bulk_commit();
+    }
+}
+
 template <int BN, int MODE, int CAP = 8>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   void* __restrict__ out, int rowsA, int rowsB, int K, int splits, int ldo,
-                  int ld_rows, const RopeEpi rope) {
+                  int ld_rows, const RopeEpi rope, const __grid_constant__ CUtensorMap tmOut, int tma_epi) {
     using Cfg = GemmCfg<BN, CAP>;
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* smemA = smem;
     uint8_t* smemB = smem + kStages * Cfg::kStageBytesA;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
@@ -522,6 +593,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;
+        float* epi_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+        if (MODE == OUT_TRANSPOSED_F32 && BN <= 64 && tma_epi && etid == 0) tma_prefetch_desc(&tmOut);
         griddep_wait();                               // `out` may still be read by the preceding kernel
         for (int it = 0; sched.next(t); ++it) {
             const int acc = it & 1;
@@ -530,11 +604,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tcgen05_fence_after();
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            epilogue_item<BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, ld_rows, rope,
-                                    reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256));
+            bool done = false;
+            if constexpr (MODE == OUT_TRANSPOSED_F32 && BN <= 64) {
+                if (tma_epi) { epilogue_planes_tma<BN>(taddr0, t, quarter, lane, etid, &tmOut, epi_stage); done = true; }
+            }
+            if (!done)
+                epilogue_item<BN, MODE>(taddr0, a_row, t, quarter, lane, out, rowsA, rowsB, ldo, ld_rows, rope, epi_stage);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if constexpr (MODE == OUT_TRANSPOSED_F32 && BN <= 64) {
+            if (tma_epi && etid == 0) bulk_wait0();   // the staging tile must outlive the stores that read it
         }
     }
 
@@ -570,7 +651,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* smemA = smem;
     uint8_t* smemB = smem + kStages * Cfg::kStageBytesA;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
@@ -578,7 +659,8 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* silu_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);
+    float* silu_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);    // exchange; aliased by the planes tile
+    __nv_bfloat16* act_stage = reinterpret_cast<__nv_bfloat16*>(smem + kStages * Cfg::kStageBytes + 256 + Cfg::kSiluStageBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     griddep_launch();
@@ -587,6 +669,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&a.tmA0); tma_prefetch_desc(&a.tmB0);
         tma_prefetch_desc(&a.tmA1); tma_prefetch_desc(&a.tmB1);
+        if (a.tma_epi) { tma_prefetch_desc(&a.tmAct); tma_prefetch_desc(&a.tmPlanes); }
     }
     if (warp == 1) {
         if (elect_one()) {
@@ -620,6 +703,8 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
             int stage = 0;
             uint32_t phase = 0;
             bool first = true;
+            int tm_i = 0;
+            trace_mark_fixed(TR_MLP_MARK + 0, tm_i++);
             for (int i = 0; get(i, t, ph); ++i) {
                 const CUtensorMap* tA = ph ? &a.tmA1 : &a.tmA0;
                 const CUtensorMap* tB = ph ? &a.tmB1 : &a.tmB0;
@@ -635,12 +720,14 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
                                      t.a_tile * BLOCK_A, polA);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                if (first) { griddep_wait(); trace_dep(tr_slot); first = false; }
+                if (first) { griddep_wait(); trace_dep(tr_slot); first = false; trace_mark_fixed(TR_MLP_MARK + 1, tm_i++); }
                 if (ph) {
                     const unsigned need = (unsigned)(t.kb1 - t.kb0);
+                    trace_mark_fixed(TR_MLP_MARK + 2, tm_i++);
                     while (ld_acquire_gpu_u32(a.ready + t.z) < need) {
                     }
                     asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy stores -> our TMA reads
+                    trace_mark_fixed(TR_MLP_MARK + 3, tm_i++);
                 }
                 for (int j = 0, s2 = st0; j < pre; ++j) {
                     tma_load_2d_hint(smemB + s2 * Cfg::kStageBytesB, tB, &full_bar[s2], (t.kb0 + j) * BLOCK_K, 0, polB);
@@ -668,6 +755,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = t.kb0; kb < t.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (kb == t.kb0) trace_mark_fixed(TR_MLP_MARK + 4 + ph, 64 + it);
                     tcgen05_fence_after();
                     const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smemA + stage * Cfg::kStageBytesA));
                     const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smemB + stage * Cfg::kStageBytesB));
@@ -692,10 +780,20 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         for (int it = 0; get(it, t, ph); ++it) {
             const int acc = it & 1;
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            if (etid == 0) trace_mark_fixed(TR_MLP_MARK + 6 + ph, 128 + 4 * it);
             tcgen05_fence_after();
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-            if (ph == 0)
+            bool tma_done = false;
+            if constexpr (BN <= 64) {
+                if (a.tma_epi) {
+                    if (ph == 0) epilogue_silu_tma<BN>(taddr0, t, quarter, lane, etid, &a.tmAct, silu_stage, act_stage);
+                    else epilogue_planes_tma<BN>(taddr0, t, quarter, lane, etid, &a.tmPlanes, silu_stage);
+                    tma_done = true;
+                }
+            }
+            if (tma_done) {
+            } else if (ph == 0)
                 epilogue_item<BN, OUT_TRANSPOSED_SILU>(taddr0, a_row, t, quarter, lane, a.act, 2 * a.inter, a.rows, a.inter, 0,
                                                        no_rope, silu_stage);
             else
@@ -704,17 +802,32 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (etid == 0) trace_mark_fixed(TR_MLP_MARK + 10, 128 + 4 * it + 1);      // stores issued
             if (ph == 0) {
                 // publish this tile's 64 act columns: every epilogue thread's stores, then one release-increment
-                asm volatile("bar.sync 3, 128;" ::: "memory");
-                if (etid == 0) {
-                    __threadfence();
-                    atomicAdd(a.ready + t.a_tile / a.slice_kb, 1u);
+                if (tma_done) {
+                    if (etid == 0) {
+                        bulk_wait0();                                                  // the bulk store's writes are performed
+                        trace_mark_fixed(TR_MLP_MARK + 11, 128 + 4 * it + 2);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __threadfence();
+                        atomicAdd(a.ready + t.a_tile / a.slice_kb, 1u);
+                        trace_mark_fixed(TR_MLP_MARK + 8, 128 + 4 * it + 3);
+                    }
+                } else {
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (etid == 0) {
+                        trace_mark_fixed(TR_MLP_MARK + 11, 128 + 4 * it + 2);          // all epilogue threads past their stores
+                        __threadfence();
+                        atomicAdd(a.ready + t.a_tile / a.slice_kb, 1u);
+                        trace_mark_fixed(TR_MLP_MARK + 8, 128 + 4 * it + 3);
+                    }
                 }
             }
         }
     }
 
+    if (a.tma_epi && threadIdx.x == 64) bulk_wait0();       // epilogue thread 0: the staging tile must outlive its stores
     tcgen05_fence_before();
     __syncthreads();
     trace_end(tr_slot);
@@ -790,7 +903,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        void* __restrict__ out, int rowsA, int rowsB, int K, int ldo, const RopeEpi rope) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* smemA = smem;
     uint8_t* smemB = smem + K2_STAGES * K2_STAGE_A;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + K2_STAGES * K2_STAGE);
@@ -960,6 +1073,34 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int rows, int K, int l
     return r == CUDA_SUCCESS ? RR_OK : RR_ERR_CUDA;
 }
 
+// planes P[z][b][n] fp32 (n contiguous, row pitch ldo, plane pitch ld_rows * ldo), valid n < n_valid, b < rows_valid:
+// 3-D map {n, b, z}, box {128, box_rows, 1}, no swizzle -- the destination of epilogue_planes_tma
+int make_tmap_planes_f32(CUtensorMap* map, const void* base, int n_valid, int ldo, int rows_valid, int ld_rows, int splits, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return RR_ERR_CUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)n_valid, (cuuint64_t)rows_valid, (cuuint64_t)splits};
+    cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)ld_rows * ldo * 4};
+    cuuint32_t box[3] = {128, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? RR_OK : RR_ERR_CUDA;
+}
+// act[b][n] bf16 (row pitch ld): 2-D map {n, b}, box {64, box_rows}, no swizzle -- the destination of epilogue_silu_tma
+int make_tmap_act_store(CUtensorMap* map, const void* base, int rows, int n, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return RR_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? RR_OK : RR_ERR_CUDA;
+}
+
 static std::atomic<int> g_num_sms[64];
 int num_sms() {                         // of the current device (one process may drive several)
     int dev = 0;
@@ -983,7 +1124,7 @@ static int launch_one(const GemmPlan& p, cudaStream_t st) {
     const int n_work = tilesA * tilesB * p.splits;
     const int grid = n_work < num_sms() ? n_work : num_sms();
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, MODE, CAP>(), st, p.tmA, p.tmB,
-                                p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows, p.rope);
+                                p.out, p.rowsA, p.rowsB, p.K, p.splits, p.ldo, p.ld_rows, p.rope, p.tmOut, p.tma_epi);
     return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? RR_OK : RR_ERR_CUDA;
 }
 
@@ -1010,6 +1151,13 @@ int gemm_plan_init(GemmPlan* p, const void* A, int rowsA, int ldA, const void* B
     int rc = make_tmap_bf16_2d(&p->tmA, A, rowsA, K, ldA, BLOCK_A);
     if (rc != RR_OK) return rc;
     // prefill orientation with 256-wide tiles and at least one full 256-row pair: 2-CTA kernel (B box = 128 rows)
+    // decode planes through one TMA store per item: needs 16-byte pitches and at most 64 batch columns per tile
+    p->tma_epi = 0;
+    if (mode == OUT_TRANSPOSED_F32 && bn <= 64 && ldo % 4 == 0 && ((uintptr_t)out & 15) == 0 && !getenv("RR_NO_TMA_EPI")) {
+        rc = make_tmap_planes_f32(&p->tmOut, out, rowsA, ldo, rowsB, ld_rows > 0 ? ld_rows : rowsB, splits, bn);
+        if (rc != RR_OK) return rc;
+        p->tma_epi = 1;
+    }
     p->two_cta = (bn == 256 && !decode_orient_rt(mode) && rowsA >= 256) ? 1 : 0;
     if (p->two_cta) {
         rc = make_tmap_bf16_2d(&p->tmB2, B, rowsB, K, ldB, 128);
@@ -1070,29 +1218,46 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
 
 
 // ---- fused decode MLP: host side ------------------------------------------------------------------
-// Greedy list schedule in units of k-blocks (+ a fixed per-item cost for pipeline refill / epilogue): gate/up tile t
-// goes to CTA t % grid (wave order: tile t is finished before tile t + grid); the down items, slice by slice (slices
-// become ready in that order), go to the least-loaded CTA.
+// List schedule on a time line in units of k-blocks (one 16 KB weight tile at a CTA's fair share of the HBM rate, 0.37 us;
+// + a fixed per-item cost for pipeline refill / epilogue).  Gate/up tile t goes to CTA t % grid (wave order: tile t is
+// finished before tile t + grid).  A slice becomes READY kPublish units after its last gate/up tile finished its mainloop --
+// the measured epilogue -> TMA store -> fence -> counter -> acquire chain (tools/trace_mlp.py: ~10 us).  The down items, slice by
+// slice, go to the CTA that can START them first, max(CTA free, slice ready); among CTAs that would all wait, the one that
+// has been free for the shortest time (best fit).  With the earlier "least loaded CTA" rule every early slice went to the CTAs
+// that own one gate/up tile, and the CTAs that own two found only late slices when they finished: they all stalled for one
+// publish latency (RR_MLP_SCHED_P=0 restores that rule).
 int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items) {
     const int tiles0 = (2 * inter) / BLOCK_A, kb0n = (hidden + BLOCK_K - 1) / BLOCK_K;
     const int tiles1 = (hidden + BLOCK_A - 1) / BLOCK_A, kb1n = inter / BLOCK_K;
     const int n_slices = (kb1n + slice_kb - 1) / slice_kb;
     constexpr int kItemCost = 6;
+    const char* pe = getenv("RR_MLP_SCHED_P");
+    const long long kPublish = pe ? atoi(pe) : 27;
     std::vector<std::vector<MlpItem>> per(grid);
     std::vector<long long> load(grid, 0);
+    std::vector<long long> tile_done(tiles0, 0);
     for (int t = 0; t < tiles0; ++t) {
         MlpItem it; it.tile_phase = t; it.kb0 = 0; it.kb1 = kb0n; it.z = 0;
         per[t % grid].push_back(it);
         load[t % grid] += kb0n + kItemCost;
+        tile_done[t] = load[t % grid];
     }
     for (int z = 0; z < n_slices; ++z) {
         const int k0 = z * slice_kb, k1 = (k0 + slice_kb < kb1n) ? k0 + slice_kb : kb1n;
+        long long ready = 0;
+        if (kPublish > 0) {
+            for (int t = k0; t < k1 && t < tiles0; ++t) ready = tile_done[t] > ready ? tile_done[t] : ready;
+            ready += kPublish;
+        }
         for (int tl = 0; tl < tiles1; ++tl) {
             int best = 0;
-            for (int c = 1; c < grid; ++c) if (load[c] < load[best]) best = c;
+            for (int c = 1; c < grid; ++c) {
+                const long long sc = load[c] > ready ? load[c] : ready, sb = load[best] > ready ? load[best] : ready;
+                if (sc < sb || (sc == sb && load[c] > load[best])) best = c;
+            }
             MlpItem it; it.tile_phase = tl | (1 << 16); it.kb0 = k0; it.kb1 = k1; it.z = z;
             per[best].push_back(it);
-            load[best] += (k1 - k0) + kItemCost;
+            load[best] = (load[best] > ready ? load[best] : ready) + (k1 - k0) + kItemCost;
         }
     }
     size_t mx = 1;
@@ -1118,6 +1283,14 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
     a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
     a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
     p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
+    a.tma_epi = 0;
+    if (bn <= 64 && hidden % 4 == 0 && inter % 8 == 0 && ((uintptr_t)planes & 15) == 0 && ((uintptr_t)act & 15) == 0 &&
+        !getenv("RR_NO_TMA_EPI")) {
+        rc = make_tmap_act_store(&a.tmAct, act, rows, inter, inter, bn);
+        if (rc == RR_OK) rc = make_tmap_planes_f32(&a.tmPlanes, planes, hidden, hidden, rows, ld_rows, p->n_slices, bn);
+        if (rc != RR_OK) return rc;
+        a.tma_epi = 1;
+    }
     return RR_OK;
 }
 
@@ -1125,8 +1298,10 @@ template <int BN>
 static int launch_mlp_bn(const MlpPlan& p, cudaStream_t st) {
     auto kern = gemm_mlp_tcgen05<BN>;
     static std::atomic<uint64_t> attr_set{0};
-    if (ensure_dyn_smem(kern, (int)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), attr_set) != cudaSuccess) return RR_ERR_CUDA;
-    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)gemm_smem_bytes<BN, OUT_TRANSPOSED_SILU>(), st, p.args);
+    constexpr int smem = GemmCfg<BN>::kSmemBytes + mlp_stage_bytes<BN>();
+    static_assert(smem <= 227 * 1024, "fused MLP kernel: shared memory budget");
+    if (ensure_dyn_smem(kern, smem, attr_set) != cudaSuccess) return RR_ERR_CUDA;
+    cudaError_t e = launch_pdl(kern, dim3(p.grid), dim3(GEMM_THREADS), (size_t)smem, st, p.args);
     return e == cudaSuccess ? RR_OK : RR_ERR_CUDA;
 }
 // Requires all CTAs co-resident (grid <= SM count; one CTA per SM by shared memory) and ready[] zero at launch.
@@ -1141,5 +1316,6 @@ int mlp_launch(const MlpPlan& p, cudaStream_t st) {
 }
 
 void rr_trace_set_gemm(unsigned long long* p) { rr_trace_set_local(p); }
+void rr_trace_set_gemm_detail(int on) { rr_trace_set_detail_local(on); }
 
 }  // namespace rr

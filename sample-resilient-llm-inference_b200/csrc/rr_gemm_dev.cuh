@@ -26,15 +26,27 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int kSiluStageBytes = 2 * 32 * 64 * 4;   // OUT_TRANSPOSED_SILU: up-row exchange, 2 x [32 cols][64 rows] fp32
 };
+// TMA-store epilogues of the decode orientation (BN <= 64): the planes tile [BN][128] fp32 (one 3-D TMA store per item); the
+// fused MLP kernel aliases it with the up-row exchange (16 KB) + the act tile [BN][64] bf16 of the SiLU epilogue.
+template <int BN>
+constexpr int planes_stage_bytes() { return BN <= 64 ? BN * 128 * 4 : 0; }
+template <int BN>
+constexpr int mlp_stage_bytes() {
+    constexpr int a = planes_stage_bytes<BN>(), b = GemmCfg<BN>::kSiluStageBytes + (BN <= 64 ? BN * 64 * 2 : 0);
+    return a > b ? a : b;
+}
 template <int MODE>
 __host__ __device__ constexpr bool decode_orient() { return MODE == OUT_TRANSPOSED_F32 || MODE == OUT_TRANSPOSED_SILU; }
 template <int BN, int MODE, int CAP = 8>
 constexpr int gemm_smem_bytes() {
     // SILU (decode): up-row exchange; RESID (prefill): per-warp 32 x 36 fp32 transpose tiles (18 KB) -- same slot
     return GemmCfg<BN, CAP>::kSmemBytes +
-           (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN, CAP>::kSiluStageBytes : MODE == OUT_ROWMAJOR_RESID ? 4 * 32 * 36 * 4 : 0);
+           (MODE == OUT_TRANSPOSED_SILU ? GemmCfg<BN, CAP>::kSiluStageBytes : MODE == OUT_ROWMAJOR_RESID ? 4 * 32 * 36 * 4 :
+            MODE == OUT_TRANSPOSED_F32 ? planes_stage_bytes<BN>() : 0);
 }
-__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.f + __expf(-g)) * u; }
+// SiLU(g) * u.  __fdividef, not `/`: the IEEE division compiles to a convergence-barrier region with a slow-path CALL per element,
+// which serialises the unrolled epilogue loops (2 ulp of fp32 before the bf16 rounding; 0 instead of -1e-36 for g < -87).
+__device__ __forceinline__ float silu_mul(float g, float u) { return __fdividef(g, 1.f + __expf(-g)) * u; }
 
 struct WorkItem {
     int a_tile, b_tile, z, kb0, kb1;

@@ -51,6 +51,8 @@ struct GemmPlan {
     RopeEpi rope;             // OUT_ROWMAJOR_ROPE only
     CUtensorMap tmB2;         // 2-CTA kernel: B with a 128-row box (each CTA of the pair stages half of the 256 rows)
     int two_cta;
+    CUtensorMap tmOut;        // OUT_TRANSPOSED_F32: planes [splits][rowsB][rowsA] (3-D, box {128, bn, 1}) for the TMA-store epilogue
+    int tma_epi;              // 1: the epilogue stages the tile in shared memory and issues ONE TMA store per item
 };
 
 int num_sms();
@@ -87,6 +89,8 @@ struct MlpArgs {
     int max_items;
     unsigned* ready;          // [n_slices], zero at launch
     int slice_kb;
+    CUtensorMap tmAct, tmPlanes;   // TMA-store epilogues: act [rows][inter] bf16 (box {64, bn}), planes (3-D, box {128, bn, 1})
+    int tma_epi;
 };
 struct MlpPlan {
     MlpArgs args;

@@ -68,7 +68,7 @@ decode_layer_tcgen05(const __grid_constant__ LayerArgs a) {
     constexpr int kStages = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = align_smem_1024(smem_raw);
     uint8_t* smemA = smem;
     uint8_t* smemB = smem + kStages * Cfg::kStageBytesA;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);

@@ -38,6 +38,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// 1024-byte aligned start of the dynamic shared memory (128B-swizzled TMA tiles / UMMA descriptors need it).  Pointer
+// arithmetic on the __shared__ array itself: rounding the pointer up through uintptr_t loses the address space and every access
+// through the result becomes a GENERIC load / store (LD.E / ST.E instead of LDS / STS), which the compiler must also keep in
+// program order against each other -- the SiLU epilogue of the decode MLP ran at 220 cycles per element because of that.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+    return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -103,6 +110,23 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// ---- TMA stores (shared -> global, bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the committed bulk stores of this thread have READ their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
