@@ -412,8 +412,10 @@ __device__ __forceinline__ void epilogue_planes_tma(uint32_t taddr0, const WorkI
     }
 }
 
-// SiLU tile of the gate/up projection: lanes 0..63 of the accumulator = gate rows, 64..127 = the matching up rows (exchanged
-// through `exch`); act_stage[b][n64] bf16  ->  act[b][a_tile * 64 + n64]
+// SiLU tile of the gate/up projection: lanes 0..63 of the accumulator = gate rows, 64..127 = the matching up rows.  ALL four
+// warps compute: per 32-column chunk the gate thread of a feature hands its columns 16..31 to the up thread and receives the up
+// values of columns 0..15 (exch: two [16][64] fp32 halves per chunk, double-buffered), so each thread evaluates 16 SiLUs per
+// chunk instead of the gate threads 32.  act_stage[b][n64] bf16  ->  act[b][a_tile * 64 + n64]
 template <int BN>
 __device__ __forceinline__ void epilogue_silu_tma(uint32_t taddr0, const WorkItem& t, int quarter, int lane, int etid,
                                                   const CUtensorMap* tmAct, float* exch, __nv_bfloat16* act_stage) {
@@ -423,19 +425,31 @@ __device__ __forceinline__ void epilogue_silu_tma(uint32_t taddr0, const WorkIte
     epi_bar();
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
-        float* buf = exch + ((c >> 5) & 1) * (32 * 64);
+        float* buf = exch + ((c >> 5) & 1) * (32 * 64);     // [0, 16) rows: up values of cols 0..15; [16, 32): gate values of cols 16..31
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr0 + c, v);
         tmem_ld_wait();
         if (is_up) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) buf[j * 64 + r64] = __uint_as_float(v[j]);
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (!is_up) {
+        float o[16];
+        if (is_up) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                act_stage[(c + j) * 64 + r64] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), buf[j * 64 + r64]));
+            for (int j = 0; j < 16; ++j) o[j] = buf[(16 + j) * 64 + r64];          // gate values, cols 16..31
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                act_stage[(c + 16 + j) * 64 + r64] = __float2bfloat16(silu_mul(o[j], __uint_as_float(v[16 + j])));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = buf[j * 64 + r64];                 // up values, cols 0..15
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                act_stage[(c + j) * 64 + r64] = __float2bfloat16(silu_mul(__uint_as_float(v[j]), o[j]));
         }
     }
     fence_proxy_async();
