@@ -264,7 +264,7 @@ static int enqueue_decode_step(rr_engine* e, cudaStream_t s, uint64_t* n_launch)
         const void* nw = (l + 1 < L) ? e->norm_attn[l + 1] : e->final_norm;
         if (e->fuse_mlp) {
             launch_add_rmsnorm(e->x, part_f32(e->part_o, e->s_o, B, d.hidden), (const __nv_bfloat16*)e->norm_mlp[l],
-                               e->xn, B, d.hidden, d.rms_eps, s, e->mlp_ready, e->mlp_slices); ++nl;
+                               e->xn, B, d.hidden, d.rms_eps, s, e->mlp_ready, e->mlp_slices + 1); ++nl;
             if (mlp_launch(e->mlp[l], s) != RR_OK) return RR_CUDA_ERROR; ++nl;
             launch_add_rmsnorm(e->x, part_f32(e->part_down, e->mlp_slices, B, d.hidden), (const __nv_bfloat16*)nw, e->xn, B,
                                d.hidden, d.rms_eps, s); ++nl;
@@ -821,14 +821,15 @@ RR_API int rr_engine_create(const rr_model_desc* desc, const rr_model_weights* w
     if (e->fuse_mlp) {
         std::vector<MlpItem> sched;
         const int grid = num_sms();
-        const int max_items = mlp_schedule(grid, d.inter, d.hidden, e->mlp_slice_kb, &sched);
+        const int dyn = getenv("RR_MLP_STATIC") ? 0 : 1;      // down items dealt by the kernel (default) or by the host list schedule
+        const int max_items = mlp_schedule(grid, d.inter, d.hidden, e->mlp_slice_kb, &sched, dyn);
         TRY(dalloc(e, &e->mlp_items, sched.size()));
         TRYC(cudaMemcpy(e->mlp_items, sched.data(), sched.size() * sizeof(MlpItem), cudaMemcpyHostToDevice));
-        TRY(dalloc(e, &e->mlp_ready, 8));
+        TRY(dalloc(e, &e->mlp_ready, 16));
         e->mlp.resize(L);
         for (int l = 0; l < L; ++l) {
             TRY(mlp_plan_init(&e->mlp[l], e->wgu[l], e->wdown[l], d.inter, d.hidden, e->xn, B, e->act, e->part_down, B,
-                              e->bn_dec, e->mlp_items, max_items, grid, e->mlp_ready, e->mlp_slice_kb));
+                              e->bn_dec, e->mlp_items, max_items, grid, e->mlp_ready, e->mlp_slice_kb, dyn));
         }
     }
     TRYC(cudaDeviceSynchronize());

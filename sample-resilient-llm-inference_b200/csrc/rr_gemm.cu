@@ -673,6 +673,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    volatile int* dyn_q = reinterpret_cast<volatile int*>(smem + kStages * Cfg::kStageBytes + 176);   // [16] dynamic down items of this CTA
     float* silu_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);    // exchange; aliased by the planes tile
     __nv_bfloat16* act_stage = reinterpret_cast<__nv_bfloat16*>(smem + kStages * Cfg::kStageBytes + 256 + Cfg::kSiluStageBytes);
 
@@ -689,6 +690,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         if (elect_one()) {
             for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
             for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+            for (int s = 0; s < 16; ++s) dyn_q[s] = -2;
             fence_barrier_init();
         }
         __syncwarp();
@@ -707,6 +709,31 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         ph = v.x >> 16; t.a_tile = v.x & 0xffff; t.b_tile = 0; t.kb0 = v.y; t.kb1 = v.z; t.z = v.w;
         return true;
     };
+    // Down items are not in the static lists when a.dyn: after its gate/up tiles a CTA takes the next item q of the slice-major
+    // order (z = q / tiles1) from a global counter, so the split follows the real finishing order instead of a host-side time
+    // model (the static list schedule left a 10 us tail: CTAs with three down items next to CTAs with one).  The producer thread
+    // draws q -- when the last load of the current item is out, so the round trip of the atomic overlaps the drain of the ring and
+    // no CTA sits on an item it cannot start -- and publishes it to the MMA / epilogue warps through dyn_q[] (-2 = not drawn yet,
+    // -1 = no more work).  Which CTA computes an item does not change a single bit of its plane tile.
+    auto dyn_decode = [&](int q, WorkItem& t, int& ph) {
+        const int z = q / a.tiles1;
+        t.a_tile = q - z * a.tiles1; t.b_tile = 0; t.kb0 = z * a.slice_kb;
+        t.kb1 = min(t.kb0 + a.slice_kb, a.kb1n); t.z = z; ph = 1;
+    };
+    auto next_consumer = [&](int it, int& nstat, WorkItem& t, int& ph) -> bool {
+        if (nstat < 0) {
+            if (get(it, t, ph)) return true;
+            nstat = it;
+        }
+        if (!a.dyn) return false;
+        const int d = it - nstat;
+        if (d >= 16) return false;
+        int q;
+        do { q = dyn_q[d]; } while (q == -2);
+        if (q < 0) return false;
+        dyn_decode(q, t, ph);
+        return true;
+    };
     WorkItem t;
     int ph = 0;
 
@@ -719,7 +746,22 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
             bool first = true;
             int tm_i = 0;
             trace_mark_fixed(TR_MLP_MARK + 0, tm_i++);
-            for (int i = 0; get(i, t, ph); ++i) {
+            int nstat = -1;
+            unsigned q_next = 0;
+            bool have_next = false;
+            for (int i = 0;; ++i) {
+                if (nstat < 0 && !get(i, t, ph)) nstat = i;
+                if (nstat >= 0) {
+                    if (!a.dyn) break;
+                    const int d = i - nstat;
+                    if (d >= 16) break;
+                    if (first) { griddep_wait(); trace_dep(tr_slot); first = false; }    // the counter is zeroed by the preceding kernel
+                    const unsigned q = have_next ? q_next : atomicAdd(a.ready + a.n_slices, 1u);
+                    have_next = false;
+                    if (q >= (unsigned)a.n_down) { dyn_q[d] = -1; break; }
+                    dyn_q[d] = (int)q;
+                    dyn_decode((int)q, t, ph);
+                }
                 const CUtensorMap* tA = ph ? &a.tmA1 : &a.tmA0;
                 const CUtensorMap* tB = ph ? &a.tmB1 : &a.tmB0;
                 // weight tiles of the first stages go out before the activations are known to exist: at the start
@@ -754,6 +796,12 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
                     tma_load_2d_hint(smemB + stage * Cfg::kStageBytesB, tB, &full_bar[stage], kb * BLOCK_K, 0, polB);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                if (a.dyn) {                       // the next item is a dynamic one: draw it now
+                    WorkItem tn; int pn;
+                    const bool next_static = nstat < 0 && get(i + 1, tn, pn);
+                    const int dn = nstat < 0 ? 0 : i + 1 - nstat;
+                    if (!next_static && dn < 16) { q_next = atomicAdd(a.ready + a.n_slices, 1u); have_next = true; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -762,7 +810,8 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
             constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_A, BN);
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; get(it, t, ph); ++it) {
+            int nstat = -1;
+            for (int it = 0; next_consumer(it, nstat, t, ph); ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
@@ -791,7 +840,8 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         no_rope.q_out = nullptr; no_rope.k_cache = nullptr; no_rope.v_cache = nullptr; no_rope.slot = nullptr;
         no_rope.pos = nullptr; no_rope.table = nullptr; no_rope.n_heads = 0; no_rope.n_kv_heads = 0; no_rope.ctx_max = 0;
         griddep_wait();
-        for (int it = 0; get(it, t, ph); ++it) {
+        int nstat = -1;
+        for (int it = 0; next_consumer(it, nstat, t, ph); ++it) {
             const int acc = it & 1;
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             if (etid == 0) trace_mark_fixed(TR_MLP_MARK + 6 + ph, 128 + 4 * it);
@@ -1240,7 +1290,7 @@ int gemm_launch(const GemmPlan& p, cudaStream_t st) {
 // has been free for the shortest time (best fit).  With the earlier "least loaded CTA" rule every early slice went to the CTAs
 // that own one gate/up tile, and the CTAs that own two found only late slices when they finished: they all stalled for one
 // publish latency (RR_MLP_SCHED_P=0 restores that rule).
-int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items) {
+int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items, int dynamic) {
     const int tiles0 = (2 * inter) / BLOCK_A, kb0n = (hidden + BLOCK_K - 1) / BLOCK_K;
     const int tiles1 = (hidden + BLOCK_A - 1) / BLOCK_A, kb1n = inter / BLOCK_K;
     const int n_slices = (kb1n + slice_kb - 1) / slice_kb;
@@ -1256,7 +1306,7 @@ int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpI
         load[t % grid] += kb0n + kItemCost;
         tile_done[t] = load[t % grid];
     }
-    for (int z = 0; z < n_slices; ++z) {
+    for (int z = 0; z < (dynamic ? 0 : n_slices); ++z) {          // dynamic: the kernel deals the down items itself
         const int k0 = z * slice_kb, k1 = (k0 + slice_kb < kb1n) ? k0 + slice_kb : kb1n;
         long long ready = 0;
         if (kPublish > 0) {
@@ -1284,7 +1334,7 @@ int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpI
 
 int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hidden, const void* xn, int rows,
                   void* act, void* planes, int ld_rows, int bn, const MlpItem* items_dev, int max_items, int grid,
-                  unsigned* ready, int slice_kb) {
+                  unsigned* ready, int slice_kb, int dynamic) {
     if (!p || !Wgu || !Wd || !xn || !act || !planes || !items_dev || !ready) return RR_ERR_ARG;
     if (inter % 64 || (2 * inter) % BLOCK_A || hidden % 8 || rows > bn || bn < 32 || slice_kb < 1) return RR_ERR_ARG;
     if ((2 * inter) / BLOCK_A > 0xffff || grid < 1 || grid > num_sms()) return RR_ERR_ARG;
@@ -1296,6 +1346,8 @@ int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hi
     if (rc != RR_OK) return rc;
     a.act = (__nv_bfloat16*)act; a.out1 = (float*)planes; a.inter = inter; a.hidden = hidden; a.rows = rows;
     a.ld_rows = ld_rows; a.items = items_dev; a.max_items = max_items; a.ready = ready; a.slice_kb = slice_kb;
+    a.kb1n = inter / BLOCK_K; a.tiles1 = (hidden + BLOCK_A - 1) / BLOCK_A;
+    a.n_slices = (a.kb1n + slice_kb - 1) / slice_kb; a.n_down = a.n_slices * a.tiles1; a.dyn = dynamic ? 1 : 0;
     p->grid = grid; p->bn = bn; p->n_slices = (inter / BLOCK_K + slice_kb - 1) / slice_kb;
     a.tma_epi = 0;
     if (bn <= 64 && hidden % 4 == 0 && inter % 8 == 0 && ((uintptr_t)planes & 15) == 0 && ((uintptr_t)act & 15) == 0 &&

@@ -87,8 +87,9 @@ struct MlpArgs {
     int inter, hidden, rows, ld_rows;
     const MlpItem* items;     // [grid][max_items]
     int max_items;
-    unsigned* ready;          // [n_slices], zero at launch
+    unsigned* ready;          // [n_slices + 1], zero at launch; the last word is the dynamic down-item counter
     int slice_kb;
+    int dyn, n_down, tiles1, kb1n, n_slices;   // dyn: down items drawn from ready[n_slices] in slice-major order (not in `items`)
     CUtensorMap tmAct, tmPlanes;   // TMA-store epilogues: act [rows][inter] bf16 (box {64, bn}), planes (3-D, box {128, bn, 1})
     int tma_epi;
 };
@@ -97,10 +98,10 @@ struct MlpPlan {
     int grid, bn, n_slices;
 };
 // Host schedule: `items` gets grid * max_items entries (CTA-major); returns max_items.
-int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items);
+int mlp_schedule(int grid, int inter, int hidden, int slice_kb, std::vector<MlpItem>* items, int dynamic = 0);
 int mlp_plan_init(MlpPlan* p, const void* Wgu, const void* Wd, int inter, int hidden, const void* xn, int rows,
                   void* act, void* planes, int ld_rows, int bn, const MlpItem* items_dev, int max_items, int grid,
-                  unsigned* ready, int slice_kb);
+                  unsigned* ready, int slice_kb, int dynamic = 0);
 int mlp_launch(const MlpPlan& p, cudaStream_t st);
 
 // ---- persistent decode layer (rr_layer.cu): O -> (+residual, deferred norm) -> gate/up+SiLU -> down -> (+residual,
