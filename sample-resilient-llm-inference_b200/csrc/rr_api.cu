@@ -53,6 +53,7 @@ void rr_trace_set_elementwise(unsigned long long*);
 void rr_trace_set_layer(unsigned long long*);
 void rr_trace_set_layer_detail(int);
 void rr_trace_set_gemm_detail(int);
+void rr_trace_set_attn_decode_detail(int);
 }
 static unsigned long long* g_trace_dev = nullptr;
 static int g_trace_cap = 0;
@@ -97,6 +98,7 @@ RR_API int rr_debug_trace_detail(int on) {
     g_trace_detail_on = on ? 1 : 0;
     rr_trace_set_layer_detail(on ? 1 : 0);
     rr_trace_set_gemm_detail(on ? 1 : 0);
+    rr_trace_set_attn_decode_detail(on ? 1 : 0);
     return check_last();
 }
 

@@ -69,6 +69,9 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     const int tr_slot = trace_begin(TR_ATTN_DEC);
     const int kvh = blockIdx.x, row = blockIdx.y, split = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // detail trace: (row 0 | 21 | 42 | 63, kv head 0); the fixed slots keep the last launch (tools/trace_attn.py)
+    const int tsm = (kvh == 0 && split == 0 && row % 21 == 0) ? row / 21 : -1;
+    if (tsm >= 0 && tid == 0) trace_mark_at(TR_ATTN_MARK + 0, 4 + tsm, 0);
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 4); }
         mbar_init(newkv_bar, 1);
@@ -115,6 +118,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
         if (leader)
             for (int u = 0; u < first; ++u) issue(u);
         griddep_wait();                         // q / new k / new v come from the QKV GEMM
+        if (tsm >= 0 && lane == 0) trace_mark_at(TR_ATTN_MARK + 1, 4 + tsm, 1);
         if (a.fuse_rope) {
             // K6 fused.  Rotated queries of the G heads -> smem (lane owns rotation pairs i = 2*lane, 2*lane+1 of
             // every head); if this CTA holds token `pos`: rotate the new key, append k / v (bf16) to the cache and
@@ -164,6 +168,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
                     v0.x += tk[zz][2].x; v0.y += tk[zz][2].y; v1.x += tk[zz][3].x; v1.y += tk[zz][3].y;
                 }
             }
+            if (tsm >= 0 && lane == 0) trace_mark_at(TR_ATTN_MARK + 2, 4 + tsm, 2);
             // smem rows are 128 wide: zero the padding beyond the true head dim first
             if (hd < HD) {
 #pragma unroll
@@ -202,11 +207,13 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(newkv_bar);      // q (and the new k / v row) are in smem
+            if (tsm >= 0 && lane == 0) trace_mark_at(TR_ATTN_MARK + 3, 4 + tsm, 3);
         }
         if (leader)
             for (int u = first; u < n_units; ++u) {
                 mbar_wait(&empty_bar[u % RING], ((u / RING) - 1) & 1);
                 issue(u);
+                if (tsm >= 0) trace_mark_at(TR_ATTN_MARK + 4, 4 + tsm, 8 + u);
             }
         return;
     }
@@ -241,12 +248,14 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // heads 2t and 2t+1
     const uint32_t ring_u = smem_u32(ring);
 
+    if (tsm >= 0 && tid == 0) trace_mark_at(TR_ATTN_MARK + 5, 4 + tsm, 4);
     for (int tile = tile0; tile < tile1; ++tile) {
         const int u = 2 * (tile - tile0);
         // ---- S^T = K Q^T for this warp's 16 tokens
         {
             const int s = u % RING;
             mbar_wait(&full_bar[s], (u / RING) & 1);
+            if (tsm >= 0 && tid == 0) trace_mark_at(TR_ATTN_MARK + 6, 4 + tsm, 64 + u);
             const uint32_t base = ring_u + s * UNIT_BYTES;
             if (tile == patch_tile && patch_warp) {          // the cache row of `pos` was written after/while TMA read it
                 if (lane < 16)
@@ -314,6 +323,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     }
 
     // ---- merge the 4 warps' states (ring memory is free: every unit was consumed by every warp)
+    if (tsm >= 0 && tid == 0) trace_mark_at(TR_ATTN_MARK + 7, 4 + tsm, 5);
     asm volatile("bar.sync 1, 128;" ::: "memory");          // consumer warps only
     float* red_o = reinterpret_cast<float*>(ring);          // [4 warps][8 heads][128]
     float* red_ml = red_o + 4 * 8 * HD;                     // [4][8][2]
@@ -357,6 +367,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
             if (dp == 0) { w[HD] = M; w[HD + 1] = L; }
         }
     }
+    if (tsm >= 0 && tid == 0) trace_mark_at(TR_ATTN_MARK + 8, 4 + tsm, 6);
     trace_end(tr_slot);
 }
 
@@ -422,5 +433,6 @@ void launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t st) {
 }
 
 void rr_trace_set_attn_decode(unsigned long long* p) { rr_trace_set_local(p); }
+void rr_trace_set_attn_decode_detail(int on) { rr_trace_set_detail_local(on); }
 
 }  // namespace rr

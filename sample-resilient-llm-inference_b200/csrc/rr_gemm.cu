@@ -629,7 +629,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         if constexpr (MODE == OUT_TRANSPOSED_F32 && BN <= 64) {
-            if (tma_epi && etid == 0) bulk_wait0();   // the staging tile must outlive the stores that read it
+            if (tma_epi && etid == 0) bulk_wait_read0();   // the staging tile must outlive the reads of its stores; grid completion covers the writes
         }
     }
 
@@ -891,7 +891,7 @@ gemm_mlp_tcgen05(const __grid_constant__ MlpArgs a) {
         }
     }
 
-    if (a.tma_epi && threadIdx.x == 64) bulk_wait0();       // epilogue thread 0: the staging tile must outlive its stores
+    if (a.tma_epi && threadIdx.x == 64) bulk_wait_read0();  // epilogue thread 0: the staging tile must outlive the reads of its stores
     tcgen05_fence_before();
     __syncthreads();
     trace_end(tr_slot);
