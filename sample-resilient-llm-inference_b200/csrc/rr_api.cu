@@ -97,7 +97,7 @@ RR_API int rr_debug_trace_stop(unsigned long long* out, int max_entries, int* n)
 RR_API int rr_debug_trace_detail(int on) {
     g_trace_detail_on = on ? 1 : 0;
     rr_trace_set_layer_detail(on ? 1 : 0);
-    rr_trace_set_gemm_detail(on ? 1 : 0);
+    rr_trace_set_gemm_detail(on);      // 1: fused MLP kernel; 10 + s: the plain decode projection with split-K factor s
     rr_trace_set_attn_decode_detail(on ? 1 : 0);
     return check_last();
 }

@@ -7,6 +7,7 @@
 //
 // Replaces (together with rr_gemm.cu / rr_attn_tc.cu / rr_attn_decode.cu) the remote bedrock:InvokeModel call
 // (reference iam/policy.json:8; src/demo_cris.py:233-238).
+#include <stdlib.h>
 #include "rr_ptx.cuh"
 #include "rr_launch.cuh"
 #include "rr_kernels.h"
@@ -140,10 +141,110 @@ add_rmsnorm_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __re
     trace_end(tr_slot);
 }
 
+// Decode variant (<= 256 rows, fp32 planes, <= 8 of them, hidden <= 4096): one memory round trip and a register budget that
+// leaves room for the next kernel's CTA.
+//  * every load of a thread -- x and ALL split planes of both of its column groups -- is issued before the first add.  The
+//    generic kernel sums the planes in a loop whose trip count is a run-time value: the compiler keeps it rolled, the add of
+//    plane z stalls on its load and the load of plane z + 1 is only issued after it, i.e. n_splits dependent L2 round trips.
+//  * 512 threads x 88 registers: 4 warps x 88 x 32 = 11 K of the 16 K registers of each SM sub-partition, which leaves room for
+//    the 2 warps x 80 registers the next GEMM's CTA (6 warps) puts on a sub-partition.  The generic kernel runs 1024 threads x
+//    64 registers = the whole register file: on the 64 SMs that host a row, the next GEMM's CTA could not start until the norm
+//    had finished, and its weight prefetch before the PDL wait was lost on 43 % of the SMs (tools/trace_gemm.py).
+// predicated 16-byte load as a volatile asm: volatile asm statements keep their program order, so a block of these followed by
+// pin4() on every result forces "all loads issued, then one wait" (nvcc otherwise sinks each load next to its add to save
+// registers, which re-creates the dependent-round-trip chain)
+__device__ __forceinline__ float4 ldg_f4_pred(const float* p, bool pred) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w) : "l"(p), "r"((int)pred) : "memory");
+    return r;
+}
+__device__ __forceinline__ void pin4(float4& v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+
+template <int MAXV>
+__global__ void __maxnreg__(88)
+add_rmsnorm_dec_kernel(float* __restrict__ x, PartIn part, const __nv_bfloat16* __restrict__ w,
+                       __nv_bfloat16* __restrict__ xn, int hidden, float eps, unsigned* __restrict__ zero, int zero_n,
+                       float* __restrict__ rowss_out, int n_part_out) {
+    constexpr int THREADS = 512, NP = 8;
+    __shared__ float red[32];
+    __shared__ float one_s;
+    if (threadIdx.x == 0) one_s = 1.f;
+    griddep_launch();
+    const int tr_slot = trace_begin(TR_NORM);
+    const int row = blockIdx.x;
+    float* xr = x + (size_t)row * hidden;
+    uint2 wv[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
+        wv[i] = c < hidden ? *reinterpret_cast<const uint2*>(w + c) : make_uint2(0u, 0u);
+    }
+    griddep_wait();
+    trace_dep(tr_slot);
+    for (int i = blockIdx.x * THREADS + threadIdx.x; i < zero_n; i += gridDim.x * THREADS) zero[i] = 0u;
+    const int ns = part.ptr ? part.n_splits : 0;
+    float4 v[MAXV], t[MAXV][NP];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
+        const bool on = c < hidden;
+        v[i] = ldg_f4_pred(xr + c, on);
+        const float* base = reinterpret_cast<const float*>(part.ptr) + (size_t)row * part.ld + c;
+#pragma unroll
+        for (int z = 0; z < NP; ++z) t[i][z] = ldg_f4_pred(base + (size_t)z * part.split_stride, on && z < ns);
+    }
+    // ptxas re-interleaves loads and adds to save registers (even across a barrier or an empty asm), which re-creates the chain.
+    // What it cannot move: every add below is an FMA with a factor 1.0f that is read from shared memory AFTER a block barrier
+    // that follows the loads -- fma(t, 1, acc) == acc + t exactly, and no add can issue before all 18 loads have.
+    __syncthreads();
+    const float one = *reinterpret_cast<volatile float*>(&one_s);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        // same association as part_load4: (((p0 + p1) + p2) + ...) first, then x + that sum
+        float4 acc = t[i][0];
+#pragma unroll
+        for (int z = 1; z < NP; ++z) {
+            acc.x = fmaf(t[i][z].x, one, acc.x); acc.y = fmaf(t[i][z].y, one, acc.y);
+            acc.z = fmaf(t[i][z].z, one, acc.z); acc.w = fmaf(t[i][z].w, one, acc.w);
+        }
+        v[i].x += acc.x; v[i].y += acc.y; v[i].z += acc.z; v[i].w += acc.w;
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    if (ns > 0) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (threadIdx.x + i * THREADS) * 4;
+            if (c < hidden) *reinterpret_cast<float4*>(xr + c) = v[i];
+        }
+    }
+    ss = block_sum(ss, red);
+    if (rowss_out != nullptr && (int)threadIdx.x < n_part_out)
+        rowss_out[(size_t)row * n_part_out + threadIdx.x] = threadIdx.x == 0 ? ss : 0.f;
+    const float inv = rowss_out != nullptr ? 1.f : rsqrtf(ss / (float)hidden + eps);
+    __nv_bfloat16* out = xn + (size_t)row * hidden;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (threadIdx.x + i * THREADS) * 4;
+        if (c < hidden) {
+            uint2 o;
+            o.x = pack_bf16(v[i].x * inv * bf16_lo(wv[i].x), v[i].y * inv * bf16_hi(wv[i].x));
+            o.y = pack_bf16(v[i].z * inv * bf16_lo(wv[i].y), v[i].w * inv * bf16_hi(wv[i].y));
+            *reinterpret_cast<uint2*>(out + c) = o;
+        }
+    }
+    trace_end(tr_slot);
+}
+
 void launch_add_rmsnorm(float* x, PartIn part, const __nv_bfloat16* w, __nv_bfloat16* xn, int rows,
                         int hidden, float eps, cudaStream_t st, unsigned* zero, int zero_n, float* rowss_out, int n_part_out) {
     if (rows <= 0 || hidden > 8192) return;
-    if (rows <= 256)
+    const bool no_dec = getenv("RR_NO_DEC_NORM") != nullptr;     // A/B switch (tools/decode_ab.py); launches are graph-captured
+    if (rows <= 256 && hidden <= 4096 && !no_dec && (part.ptr == nullptr || (!part.is_bf16 && part.n_splits <= 8)))
+        launch_pdl(add_rmsnorm_dec_kernel<2>, dim3(rows), dim3(512), 0, st, x, part, w, xn, hidden, eps, zero, zero_n,
+                   rowss_out, n_part_out);
+    else if (rows <= 256)
         launch_pdl(add_rmsnorm_kernel<1024, 2>, dim3(rows), dim3(1024), 0, st, x, part, w, xn, hidden, eps, zero, zero_n,
                    rowss_out, n_part_out);
     else if (hidden <= 4096)      // fewer registers -> more rows in flight per SM (HBM-bound at thousands of rows)

@@ -510,6 +510,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     WorkSched sched;
     sched.init(rowsA, rowsB, K, splits, BN);
     WorkItem t;
+    // detail trace of a plain decode projection: selected by its split-K factor (rr_debug_trace_detail(10 + splits)), CTAs 0 / 37 / 74 / 111
+    const int tsm = (decode_orient<MODE>() && rr_trace_detail == 10 + splits && blockIdx.x % 37 == 0) ? 8 + (int)(blockIdx.x / 37) : -1;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -522,6 +524,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             bool have = sched.next(t);
+            if (tsm >= 0) trace_mark_at(TR_GEMM_MARK + 0, tsm, 0);
             // PDL prefetch of the constant (weight) operand for the first `pre` k-blocks.
             // (An additional L2 prefetch of the panel behind the ring was measured in round 1: whole panel 5.12 -> 5.37 ms
             //  per decode step, bounded to 8 / 16 k-blocks no gain / slower; removed.)
@@ -540,6 +543,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             griddep_wait();
             trace_dep(tr_slot);
+            if (tsm >= 0) trace_mark_at(TR_GEMM_MARK + 1, tsm, 1);
             if (have) {
                 for (int i = 0; i < pre; ++i) {
                     if (decode_orient<MODE>())
@@ -568,6 +572,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 have = sched.next(t);
             }
+            if (tsm >= 0) trace_mark_at(TR_GEMM_MARK + 2, tsm, 2);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -583,6 +588,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = t.kb0; kb < t.kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (tsm >= 0 && kb == t.kb0) trace_mark_at(TR_GEMM_MARK + 3, tsm, 8 + it);
                     tcgen05_fence_after();
                     const uint64_t adesc =
                         umma_desc_sw128_kmajor(smem_u32(smemA + stage * Cfg::kStageBytesA));
@@ -615,6 +621,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
+            if (tsm >= 0 && etid == 0) trace_mark_at(TR_GEMM_MARK + 4, tsm, 16 + 2 * it);
             tcgen05_fence_after();
             const int a_row = t.a_tile * BLOCK_A + row_in_tile;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
@@ -627,6 +634,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (tsm >= 0 && etid == 0) trace_mark_at(TR_GEMM_MARK + 5, tsm, 17 + 2 * it);
         }
         if constexpr (MODE == OUT_TRANSPOSED_F32 && BN <= 64) {
             if (tma_epi && etid == 0) bulk_wait_read0();   // the staging tile must outlive the reads of its stores; grid completion covers the writes
@@ -635,6 +643,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     tcgen05_fence_before();
     __syncthreads();
+    if (tsm >= 0 && threadIdx.x == 0) trace_mark_at(TR_GEMM_MARK + 6, tsm, 3);
     trace_end(tr_slot);
     if (warp == 1) {
         tcgen05_fence_after();

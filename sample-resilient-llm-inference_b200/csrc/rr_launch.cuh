@@ -25,7 +25,7 @@ static inline void rr_trace_set_detail_local(int on) { cudaMemcpyToSymbol(rr_tra
 enum TraceId { TR_GEMM_DEC = 1, TR_GEMM_PF = 2, TR_ATTN_DEC = 3, TR_ATTN_PF = 4, TR_NORM = 5, TR_ROPE = 6,
                TR_SILU = 7, TR_EMBED = 8, TR_ARGMAX = 9, TR_COMBINE = 10, TR_MISC = 11,
                TR_LAYER_PH0 = 12,
-               TR_MLP_MARK = 50, TR_ATTN_MARK = 80 };  // + k: sample CTAs of the fused MLP kernel (tools/trace_mlp.py)  // + k: sample CTAs of the layer kernel finished an item (0 O, 1 gate/up, 2 down, 3 reduce, 4 next)
+               TR_MLP_MARK = 50, TR_ATTN_MARK = 80, TR_GEMM_MARK = 100 };  // + k: sample CTAs of the fused MLP kernel (tools/trace_mlp.py)  // + k: sample CTAs of the layer kernel finished an item (0 O, 1 gate/up, 2 down, 3 reduce, 4 next)
 __device__ __forceinline__ unsigned long long rr_gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
