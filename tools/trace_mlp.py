@@ -31,11 +31,11 @@ a = a[a[:, 0] != 0]
 a = a[np.argsort(a[:, 1], kind="stable")]
 kid = a[:, 0] & 0xFF
 cta = a[:, 0] >> 8
-det = kid >= 50
+det = (kid >= 50) & (kid < 80)
 d = a[det]; dk = kid[det]; dc = cta[det]
 t0, t1 = d[:, 1].min(), d[:, 1].max()
 # CTA-0 records of the kernels around the marked launch (the fixed slots keep the LAST fused-MLP launch of the run)
-ker = a[~det]; kk = kid[~det]
+ker = a[kid < 50]; kk = kid[kid < 50]
 sel = (ker[:, 3] >= t0 - 60000) & (ker[:, 1] <= t1 + 30000)
 rows = [(int(r[1]), f"{NAMES.get(int(k), k):10s} start; dep resolved +{(r[2] - r[1]) / 1e3:.2f}; end +{(r[3] - r[1]) / 1e3:.2f}") for r, k in zip(ker[sel], kk[sel])]
 only = int(sys.argv[2]) if len(sys.argv) > 2 else None
