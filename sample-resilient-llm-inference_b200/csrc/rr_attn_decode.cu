@@ -16,6 +16,7 @@
 //    states are merged once at the end (and across kv splits by a small combine kernel).
 //
 // Replaces the remote bedrock:InvokeModel call (reference iam/policy.json:8).
+#include <stdlib.h>
 #include "rr_ptx.cuh"
 #include "rr_launch.cuh"
 #include "rr_kernels.h"
@@ -78,6 +79,7 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
         fence_barrier_init();
         tma_prefetch_desc(&a.tmK);
         tma_prefetch_desc(&a.tmV);
+        if (a.trim_tail) { tma_prefetch_desc(&a.tmK16); tma_prefetch_desc(&a.tmV16); }
     }
     __syncthreads();
     // Row metadata and the K/V rows of EARLIER tokens are constant for the whole step (written by previous graph
@@ -106,10 +108,26 @@ decode_attn_mma_kernel(const __grid_constant__ DecodeAttnArgs a) {
     if (warp == 4) {
         // ===================== producer: TMA units K0 V0 K1 V1 ... =====================
         const bool leader = elect_one();
+        // The last tile of a row usually holds fewer than 64 tokens: it is requested as 16-row boxes covering only the rows in use
+        // (ncu: the kernel read 1.14 x its algorithmic bytes with whole tiles).  The rows of the slot that are not rewritten keep
+        // the finite K / V data of the unit staged there before (hence u >= RING); their scores are masked, p = 0.
         auto issue = [&](int u) {
             const int s = u % RING;
-            const CUtensorMap* tm = (u & 1) ? &a.tmV : &a.tmK;
-            const int r0 = row_base + (tile0 + (u >> 1)) * DT;
+            const bool is_v = (u & 1) != 0;
+            const int tile = tile0 + (u >> 1);
+            const int r0 = row_base + tile * DT;
+            const int valid = ctx - tile * DT;                        // > 0; >= DT for all but the last tile
+            if (a.trim_tail && valid <= DT - 16 && u >= RING) {
+                const int nb = (valid + 15) >> 4;
+                const CUtensorMap* tm = is_v ? &a.tmV16 : &a.tmK16;
+                mbar_arrive_expect_tx(&full_bar[s], nb * 4096);
+                for (int b = 0; b < nb; ++b) {
+                    tma_load_2d(ring + s * UNIT_BYTES + b * 2048, tm, &full_bar[s], 0, r0 + 16 * b);
+                    tma_load_2d(ring + s * UNIT_BYTES + 8192 + b * 2048, tm, &full_bar[s], 64, r0 + 16 * b);
+                }
+                return;
+            }
+            const CUtensorMap* tm = is_v ? &a.tmV : &a.tmK;
             mbar_arrive_expect_tx(&full_bar[s], UNIT_BYTES);
             tma_load_2d(ring + s * UNIT_BYTES, tm, &full_bar[s], 0, r0);
             tma_load_2d(ring + s * UNIT_BYTES + 8192, tm, &full_bar[s], 64, r0);
@@ -405,8 +423,11 @@ int decode_attn_make_maps(DecodeAttnArgs* a, int n_slots) {
     const long long rows = (long long)n_slots * a->n_kv_heads * a->ctx_max;
     if (rows <= 0 || rows > 0x7fffffffLL || a->ctx_max % DT) return RR_ERR_ARG;
     int rc = make_tmap_bf16_2d(&a->tmK, a->k_cache, (int)rows, HD, HD, DT);
-    if (rc != RR_OK) return rc;
-    return make_tmap_bf16_2d(&a->tmV, a->v_cache, (int)rows, HD, HD, DT);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a->tmV, a->v_cache, (int)rows, HD, HD, DT);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a->tmK16, a->k_cache, (int)rows, HD, HD, 16);
+    if (rc == RR_OK) rc = make_tmap_bf16_2d(&a->tmV16, a->v_cache, (int)rows, HD, HD, 16);
+    a->trim_tail = getenv("RR_ATTN_NO_TRIM") ? 0 : 1;
+    return rc;
 }
 
 template <int G>

@@ -212,6 +212,8 @@ struct DecodeAttnArgs {
     float* ws;                // split-KV workspace (may be null when kv_splits == 1)
     int kv_splits;
     CUtensorMap tmK, tmV;     // [n_slots*n_kv_heads*ctx_max, 128] views of the caches, box {64, 64}, SW128
+    CUtensorMap tmK16, tmV16; // same views, box {64, 16}: the last tile of a row is requested in 16-row pieces
+    int trim_tail;
     // fused RoPE + KV append (decode): q/k/v of the current token come straight from the QKV GEMM's
     // split-K planes; q is rotated into the MMA fragments, k/v are rotated, appended to the cache and
     // patched into the staged tile.  fuse_rope == 0: `q` holds rotated bf16 queries (rope_kv_kernel ran).
