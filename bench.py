@@ -289,10 +289,14 @@ def kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak):
     kv_layer = C * ctx * spec.kv_bytes_per_token // L
     rows = {}
     n_gemm = 0
+    host_gap_us = 0.0
     gemm_total = int((step[:-1, 0] == 1).sum())
     for i in range(len(step) - 1):
         kid = int(step[i, 0])
         seg_us = (step[i + 1, 2] - step[i, 2]) / 1e3
+        if i == len(step) - 2:                                 # last kernel of the step (argmax): its own dependency -> end; the
+            seg_us = (step[i, 3] - step[i, 2]) / 1e3           # segment to the next step's first kernel would add the host's
+            host_gap_us = (step[i + 1, 2] - step[i, 3]) / 1e3  # graph relaunch (reported separately)
         name, nbytes = NAMES.get(kid, f"kernel {kid}"), 0
         if kid == 3:
             nbytes = kv_layer
@@ -324,6 +328,7 @@ def kernel_table(eng, spec, prompts_np, C, P, M, hbm_peak):
                     "achieved_gbs": gbs, "frac_of_hbm_peak": (gbs / hbm_peak) if gbs else None})
     out.sort(key=lambda x: -x["us_per_step"])
     return {"step_us_traced": float((step[-1, 2] - step[0, 2]) / 1e3), "ctx": ctx, "rows": out,
+            "host_gap_between_steps_us": float(host_gap_us),
             "method": "in-kernel %globaltimer stamps of CTA 0 (rr_debug_trace_*), critical-path segments inside the replayed CUDA "
                       "graph; the stamps themselves cost ~3 us per kernel (compare step_us_traced with roofline.ms_per_launch): "
                       "read the SHARES and the per-kernel fractions as lower bounds"}
