@@ -204,6 +204,19 @@ int main() {
                    b / d2 / 1e6, b / d3 / 1e6, b / d4 / 1e6, b / d8 / 1e6);
         }
     }
+    {   // fewer CTAs than SMs (the second gate/up wave of the fused MLP runs on 76, the late down items on ~96): is a lone CTA's
+        // rate set by its ring depth (bytes in flight / latency)?
+        const uint64_t Kv = 4096, rows = (bytes / 2 / Kv) / 128 * 128;
+        const int tiles = (int)(rows / 128) / 4, kblocks = (int)(Kv / 64);
+        const double b = (double)tiles * kblocks * 16384;
+        CUtensorMap strided = mk(enc, buf, rows, Kv, 1);
+        for (int g : {32, 76, 96, 148}) {
+            float d6 = run_tma<6>(strided, tiles, kblocks, 0, g, 3), d8 = run_tma<8>(strided, tiles, kblocks, 0, g, 3),
+                  d10 = run_tma<10>(strided, tiles, kblocks, 0, g, 3), d12 = run_tma<12>(strided, tiles, kblocks, 0, g, 3);
+            printf("%3d CTAs: ring 6 %5.1f  ring 8 %5.1f  ring 10 %5.1f  ring 12 %5.1f GB/s per SM\n", g, b / d6 / 1e6 / g, b / d8 / 1e6 / g,
+                   b / d10 / 1e6 / g, b / d12 / 1e6 / g);
+        }
+    }
     {   // weight stream + re-read activation stream
         const uint64_t Kv = 4096, rows = (bytes / 2 / Kv) / 128 * 128;
         const int tiles = (int)(rows / 128), kblocks = (int)(Kv / 64);
