@@ -199,6 +199,39 @@ def test_serving_loop_equals_stepwise_and_is_deterministic():
         eng.close()
 
 
+@pytest.mark.parametrize("spec_name,rows", [("small", 64), ("llama-3-8b-2l", 64), ("llama-3-8b-2l", 24)])
+def test_decode_work_distribution_and_epilogue_switches_do_not_change_tokens(spec_name, rows, monkeypatch):
+    """The fused decode MLP deals its down items dynamically (device counter) and the decode GEMMs store their tiles by TMA;
+    which CTA computes an item, and through which store path a tile leaves, must not change a single generated token:
+    same tokens as the static host schedule (RR_MLP_STATIC) and as the per-thread store epilogues (RR_NO_TMA_EPI)."""
+    import numpy as np
+    from rr_b200.models import SPECS, make_weights
+    from rr_b200.engine import Engine
+    spec = SPECS[spec_name]
+    w = make_weights(spec, seed=5, sigma=0.03, device="cuda", norm_jitter=0.1)
+    rng = np.random.RandomState(3)
+    ids = rng.randint(0, spec.vocab, size=(rows, 96)).astype(np.int32)
+    start = np.arange(0, rows * 96 + 1, 96, dtype=np.int32)
+
+    def run(env):
+        for k in ("RR_MLP_STATIC", "RR_NO_TMA_EPI"):
+            monkeypatch.delenv(k, raising=False)
+        for k in env:
+            monkeypatch.setenv(k, "1")
+        eng = Engine(w, max_batch=64, ctx_max=256, max_prefill_tokens=2048, use_cuda_graph=True)
+        try:
+            recs, toks = eng.run_batch(ids.reshape(-1), start, 12)
+            assert all(r.status == 0 for r in recs)
+            return toks.copy()
+        finally:
+            eng.close()
+
+    base = run([])
+    assert np.array_equal(base, run([])), "two default engines disagree (non-deterministic kernels?)"
+    assert np.array_equal(base, run(["RR_MLP_STATIC"]))
+    assert np.array_equal(base, run(["RR_NO_TMA_EPI"]))
+
+
 def test_run_batch_and_fault_injection():
     from rr_b200.models import SPECS, make_weights
     from rr_b200.engine import Engine

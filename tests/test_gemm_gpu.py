@@ -47,6 +47,25 @@ def test_gemm_transposed_f32(rowsA, rowsB, K, bn, splits):
     assert err <= 1e-3 * scale + 1e-4, (err, scale)
 
 
+@pytest.mark.parametrize("rowsA,rowsB,K,bn,splits,ld_rows", [(384, 33, 512, 64, 3, 64), (1000, 7, 320, 16, 2, 8), (6144, 64, 4096, 64, 3, 64),
+                                                          (4096, 20, 1024, 32, 4, 32)])
+def test_decode_gemm_tma_store_epilogue_equals_lsu_epilogue_and_clips(rowsA, rowsB, K, bn, splits, ld_rows, monkeypatch):
+    """Decode orientation: the planes tile goes out as ONE TMA store per item (3-D tensor map [split][row][feature]).  It must
+    write exactly the bits of the per-thread store epilogue (RR_NO_TMA_EPI=1, read when the plan is built) and must not touch
+    plane rows >= rowsB (the map's row extent is rowsB, not the plane pitch)."""
+    g = torch.Generator(device="cuda").manual_seed(rowsA + 31 * rowsB)
+    A = (torch.randn(rowsA, K, device="cuda", generator=g) * 0.05).bfloat16()
+    B = torch.randn(rowsB, K, device="cuda", generator=g).bfloat16()
+    monkeypatch.delenv("RR_NO_TMA_EPI", raising=False)
+    tma = _gemm(A, B, 1, bn, splits, ld_rows=ld_rows)
+    monkeypatch.setenv("RR_NO_TMA_EPI", "1")
+    lsu = _gemm(A, B, 1, bn, splits, ld_rows=ld_rows)
+    assert torch.isfinite(tma[:, :rowsB]).all()
+    assert torch.equal(tma[:, :rowsB], lsu[:, :rowsB])
+    if ld_rows > rowsB:
+        assert torch.isnan(tma[:, rowsB:]).all() and torch.isnan(lsu[:, rowsB:]).all()
+
+
 CASES_R = [(128, 256, 64, 256), (512, 6144, 4096, 256), (1000, 520, 256, 128), (2048, 4096, 4096, 256),
            (130, 72, 128, 64), (4096, 28672, 4096, 256),
            # ragged shapes through the 2-CTA pair kernel (rowsA >= 256, bn 256): partial pair tiles on both axes
