@@ -654,11 +654,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // =================================================================================================
 // Fused decode MLP: act = SiLU(x Wg^T) * (x Wu^T), planes = act Wd^T in ONE persistent launch (decode orientation,
 // weights on the UMMA M side).  Same warp roles, smem ring and TMEM double buffer as gemm_bf16_tcgen05; the pipeline
-// state simply carries from item to item.  Each CTA walks a host-built list: its gate/up tiles first, then its down
-// items.  A down item = (128 output features, one K-slice of `slice_kb` k-blocks); k-block kb of the down GEMM is
+// state simply carries from item to item.  Each CTA runs its gate/up tiles from a host-built list, then its down items:
+// drawn from a device counter (a.dyn, default) or from the same list (static schedule, RR_MLP_STATIC).
+// A down item = (128 output features, one K-slice of `slice_kb` k-blocks); k-block kb of the down GEMM is
 // exactly the 64 act columns gate/up tile kb writes, so the item only depends on the tiles of its slice: the gate/up
-// epilogue bumps ready[slice] (release, gpu scope) and the producer of a down item requests the WEIGHT tiles of its
-// first stages, then acquires ready[slice] == slice length, then requests the activation tiles.  No kernel boundary,
+// epilogue (TMA store of the act tile, completion wait, fence) bumps ready[slice] and the producer of a down item requests
+// the WEIGHT tiles of its first stages, then acquires ready[slice] == slice length, then requests the activation tiles.
+// No kernel boundary,
 // no wave-quantisation tail of the gate/up grid (224 tiles on 148 SMs): CTAs that own one gate/up tile start on the
 // early slices while the others finish their second tile.
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
